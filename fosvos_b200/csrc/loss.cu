@@ -1,0 +1,176 @@
+// Class-balanced sigmoid cross entropy, forward reduction and backward
+// (reference layers/osvos_layers.py:17-44; ~15 ATen kernels + 3 full reductions there).
+// HBM-bound: forward reads 8 B/pixel, backward reads 8 + writes 4 B/pixel; float4 accesses,
+// warp-shuffle + one double atomic per warp-group for the sums.
+#include "common.cuh"
+
+namespace fosvos {
+
+struct LossAcc {
+  float pos, s_pos, s_neg;
+};
+
+__device__ __forceinline__ void loss_elem(float x, float lab, LossAcc& a) {
+  const float y = lab >= 0.5f ? 1.f : 0.f;                 // torch.ge(label, 0.5).float()   :26
+  const float z = x >= 0.f ? 1.f : 0.f;                    // output_gt_zero                :32
+  const float lv = x * (y - z) - logf(1.f + expf(x - 2.f * x * z));   // loss_val           :33-34
+  a.pos += y;
+  a.s_pos += -(y * lv);                                    // loss_pos                      :36
+  a.s_neg += -((1.f - y) * lv);                            // loss_neg                      :37
+}
+
+__global__ void __launch_bounds__(256)
+bal_loss_fwd_kernel(const float* __restrict__ out, const float* __restrict__ lab, long long n, int size_average,
+                    double* __restrict__ stats, float* __restrict__ loss) {
+  LossAcc a{0.f, 0.f, 0.f};
+  const long long n4 = n / 4;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 x = reinterpret_cast<const float4*>(out)[i];
+    const float4 l = reinterpret_cast<const float4*>(lab)[i];
+    loss_elem(x.x, l.x, a); loss_elem(x.y, l.y, a); loss_elem(x.z, l.z, a); loss_elem(x.w, l.w, a);
+  }
+  for (long long i = n4 * 4 + tid; i < n; i += nth) loss_elem(out[i], lab[i], a);
+
+  double pos = warp_sum((double)a.pos), sp = warp_sum((double)a.s_pos), sn = warp_sum((double)a.s_neg);
+  __shared__ double sm[3][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][wid] = pos; sm[1][wid] = sp; sm[2][wid] = sn; }
+  __syncthreads();
+  if (wid == 0) {
+    pos = lane < 8 ? sm[0][lane] : 0.0;
+    sp = lane < 8 ? sm[1][lane] : 0.0;
+    sn = lane < 8 ? sm[2][lane] : 0.0;
+    pos = warp_sum(pos); sp = warp_sum(sp); sn = warp_sum(sn);
+    if (lane == 0) {
+      atomicAdd(&stats[0], pos);
+      atomicAdd(&stats[2], sp);
+      atomicAdd(&stats[3], sn);
+      __threadfence();
+      unsigned long long* counter = reinterpret_cast<unsigned long long*>(&stats[4]);
+      const unsigned long long done = atomicAdd(counter, 1ULL) + 1ULL;
+      if (done == gridDim.x) {                  // last block: finalise
+        __threadfence();
+        const double P = atomicAdd(&stats[0], 0.0), SP = atomicAdd(&stats[2], 0.0), SN = atomicAdd(&stats[3], 0.0);
+        const double Nn = (double)n - P, tot = (double)n;
+        stats[1] = Nn;
+        // fp32 like the reference: num_labels_neg / num_total * loss_pos + num_labels_pos / num_total * loss_neg  :39
+        float v = (float)Nn / (float)tot * (float)SP + (float)P / (float)tot * (float)SN;
+        if (size_average) v = v / (float)n;                                                          // :41-42
+        *loss = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bal_loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ lab, long long n, int size_average,
+                    const double* __restrict__ stats, const float* __restrict__ grad_out, float grad_scale,
+                    float* __restrict__ dx) {
+  const float tot = (float)n;
+  float g = grad_scale * (grad_out ? *grad_out : 1.f);
+  if (size_average) g /= tot;
+  const float w1 = (float)stats[1] / tot * g;   // y = 1: neg/total
+  const float w0 = (float)stats[0] / tot * g;   // y = 0: pos/total
+  auto f = [&](float x, float l) -> float {
+    const float t = expf(-fabsf(x));
+    const float s = x >= 0.f ? 1.f / (1.f + t) : t / (1.f + t);
+    return l >= 0.5f ? w1 * (s - 1.f) : w0 * s;
+  };
+  const long long n4 = n / 4;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 x = reinterpret_cast<const float4*>(out)[i];
+    const float4 l = reinterpret_cast<const float4*>(lab)[i];
+    reinterpret_cast<float4*>(dx)[i] = make_float4(f(x.x, l.x), f(x.y, l.y), f(x.z, l.z), f(x.w, l.w));
+  }
+  for (long long i = n4 * 4 + tid; i < n; i += nth) dx[i] = f(out[i], lab[i]);
+}
+
+__global__ void sigmoid_threshold_kernel(const float* __restrict__ x, float* __restrict__ prob,
+                                         uint8_t* __restrict__ mask, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float p = 1.f / (1.f + expf(-x[i]));        // util/experiment_helper.py:57
+    if (prob) prob[i] = p;
+    if (mask) mask[i] = p >= 0.5f ? 1 : 0;            // run_webcam.py:92-93
+  }
+}
+
+// |a & b| and |a | b| of two {0,1} byte masks, one (inter, union) int64 pair per frame.
+__global__ void __launch_bounds__(256)
+mask_iou_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, long long ppf, long long* __restrict__ counts) {
+  const int f = blockIdx.y;
+  const uint8_t* pa = a + (long long)f * ppf;
+  const uint8_t* pb = b + (long long)f * ppf;
+  unsigned inter = 0, uni = 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb)) & 15) == 0;
+  const long long n16 = aligned ? ppf / 16 : 0;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n16; i += nth) {
+    const uint4 va = reinterpret_cast<const uint4*>(pa)[i], vb = reinterpret_cast<const uint4*>(pb)[i];
+    const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned ma = __vcmpne4(wa[k], 0u) & 0x01010101u, mb = __vcmpne4(wb[k], 0u) & 0x01010101u;
+      inter += __popc(ma & mb);
+      uni += __popc(ma | mb);
+    }
+  }
+  for (long long i = n16 * 16 + tid; i < ppf; i += nth) {
+    const bool x = pa[i] != 0, y = pb[i] != 0;
+    inter += (x && y);
+    uni += (x || y);
+  }
+  inter = __reduce_add_sync(0xffffffffu, inter);
+  uni = __reduce_add_sync(0xffffffffu, uni);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&counts[2 * f]), (unsigned long long)inter);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&counts[2 * f + 1]), (unsigned long long)uni);
+  }
+}
+
+}  // namespace fosvos
+
+using namespace fosvos;
+
+extern "C" {
+
+int fosvos_bal_loss_fwd(const float* output, const float* label, long long numel, int size_average, double* stats,
+                        float* loss, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(output && label && stats && loss && numel > 0, "bal_loss_fwd: bad arguments");
+  FOSVOS_REQUIRE(((uintptr_t)output & 15) == 0 && ((uintptr_t)label & 15) == 0, "bal_loss_fwd: pointers must be 16-byte aligned");
+  cudaMemsetAsync(stats, 0, 8 * sizeof(double), as_stream(stream));
+  const int blocks = (int)min((long long)num_sms() * 4, ceil_div_ll(numel, 1024));
+  bal_loss_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, loss);
+  return check_launch("bal_loss_fwd");
+}
+
+int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel, int size_average,
+                        const double* stats, const float* grad_out, float grad_scale, float* dx,
+                        fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(output && label && stats && dx && numel > 0, "bal_loss_bwd: bad arguments");
+  FOSVOS_REQUIRE(((uintptr_t)output & 15) == 0 && ((uintptr_t)label & 15) == 0 && ((uintptr_t)dx & 15) == 0,
+                 "bal_loss_bwd: pointers must be 16-byte aligned");
+  const int blocks = (int)min((long long)num_sms() * 4, ceil_div_ll(numel, 1024));
+  bal_loss_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, grad_out,
+                                                            grad_scale, dx);
+  return check_launch("bal_loss_bwd");
+}
+
+int fosvos_sigmoid_threshold(const float* logits, float* prob, uint8_t* mask, long long numel, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(logits && (prob || mask) && numel > 0, "sigmoid_threshold: bad arguments");
+  const int blocks = (int)min((long long)num_sms() * 8, ceil_div_ll(numel, 256));
+  sigmoid_threshold_kernel<<<blocks, 256, 0, as_stream(stream)>>>(logits, prob, mask, numel);
+  return check_launch("sigmoid_threshold");
+}
+
+int fosvos_mask_iou(const uint8_t* a, const uint8_t* b, long long pixels_per_frame, int n_frames, long long* counts,
+                    fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(a && b && counts && pixels_per_frame > 0 && n_frames > 0, "mask_iou: bad arguments");
+  cudaMemsetAsync(counts, 0, 2 * sizeof(long long) * n_frames, as_stream(stream));
+  dim3 grid((unsigned)min((long long)64, ceil_div_ll(pixels_per_frame, 256 * 16)), n_frames);
+  mask_iou_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, b, pixels_per_frame, counts);
+  return check_launch("mask_iou");
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// 2x2 / stride-2 max pooling with ceil_mode=True over NHWC activations
+// (nn.MaxPool2d(kernel_size=2, stride=2, ceil_mode=True), reference osvos_vgg.py:90).
+// HBM-bound: one thread per (output pixel, 8-channel vector), 16/32-byte accesses,
+// consecutive threads walk consecutive channel vectors -> fully coalesced.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace fosvos {
+
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int OH, int OW,
+                                   long long total) {
+  const int groups = C / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const long long n = r / OH;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -CUDART_INF_F;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+        if (iy < H && ix < W) {                       // ceil_mode: the last window is clipped
+          float v[8];
+          load8(x + ((n * H + iy) * W + ix) * C + g * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+        }
+      }
+    store8(y + ((n * OH + oy) * OW + ox) * C + g * 8, m);
+  }
+}
+
+// Gradient goes to the FIRST maximum of the window in (row, col) scan order -- the index
+// max_pool2d_with_indices records (strict '>' comparison against a running maximum).
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int H,
+                                   int W, int C, int OH, int OW, long long total) {
+  const int groups = C / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const long long n = r / OH;
+    float v[4][8];
+    float m[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = -CUDART_INF_F; arg[j] = 0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int iy = 2 * oy + (k >> 1), ix = 2 * ox + (k & 1);
+      if (iy < H && ix < W) {
+        load8(x + ((n * H + iy) * W + ix) * C + g * 8, v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[k][j] > m[j]) { m[j] = v[k][j]; arg[j] = k; }
+      }
+    }
+    float gsrc[8];
+    load8(dy + ((n * OH + oy) * OW + ox) * C + g * 8, gsrc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int iy = 2 * oy + (k >> 1), ix = 2 * ox + (k & 1);
+      if (iy < H && ix < W) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = arg[j] == k ? gsrc[j] : 0.f;
+        store8(dx + ((n * H + iy) * W + ix) * C + g * 8, o);
+      }
+    }
+  }
+}
+
+}  // namespace fosvos
+
+using namespace fosvos;
+
+extern "C" {
+
+int fosvos_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool2x2_fwd: bad shape (C=%d must be a multiple of 8)", C);
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  const int blocks = (int)min((long long)num_sms() * 16, ceil_div_ll(total, 256));
+  FOSVOS_DISPATCH_DTYPE(dtype, T, {
+    maxpool_fwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, H, W, C, OH, OW, total);
+  });
+  return check_launch("maxpool2x2_fwd");
+}
+
+int fosvos_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
+                          fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(x && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool2x2_bwd: bad shape (C=%d must be a multiple of 8)", C);
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  const int blocks = (int)min((long long)num_sms() * 16, ceil_div_ll(total, 256));
+  FOSVOS_DISPATCH_DTYPE(dtype, T, {
+    maxpool_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)dy, (T*)dx, H, W, C, OH, OW, total);
+  });
+  return check_launch("maxpool2x2_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+"""OSVOS VGG-16 on B200: drop-in for the reference ``networks/osvos_vgg.py``.
+
+Same constructor, sub-module names, ``state_dict`` layout and ``forward`` contract as the
+reference ``OSVOS_VGG`` (``/root/reference/src/networks/osvos_vgg.py:17-83``): ``forward(x)``
+takes an NCHW fp32 frame batch and returns ``[side0, side1, side2, side3, fused]`` logit maps,
+each ``(N,1,H,W)`` fp32.  Parameters are ordinary fp32 ``nn.Parameter`` s in the reference
+layout; everything between them and the five outputs runs in hand-written sm_100a kernels
+behind the C ABI (``include/fosvos_b200.h``): NHWC activations, tcgen05 implicit-GEMM 3x3
+convolutions, a fused side-output chain.  There is no CPU path and no cuDNN path.
+
+Precision (``net.precision``):
+  'bf16'       bf16 activations/weights, fp32 accumulation in TMEM (tcgen05 kernels) -- default
+  'fp32'       fp32 activations/weights, fp32 FMA (direct kernels): the strict-parity mode
+  'bf16_simt'  bf16 data through the direct kernels (debug cross-check of the tcgen05 path)
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.modules as modules
+
+from . import _lib as L
+from . import ops
+from .layers import interp_surgery
+
+_LAY_LIST = [[64, 64], ['M', 128, 128], ['M', 256, 256, 256], ['M', 512, 512, 512], ['M', 512, 512, 512]]
+_IN_CHANNELS = [3, 64, 128, 256, 512]
+
+
+def _act_dtype(precision: str) -> torch.dtype:
+    return torch.float32 if precision == "fp32" else torch.bfloat16
+
+
+class _PackedConv:
+    """Derived kernel-side copies of one 3x3 conv's parameters (never serialised)."""
+
+    def __init__(self):
+        self.key = None
+        self.w_fwd = self.w_dgrad = self.bias = None
+
+
+class OSVOS_VGG(nn.Module):
+    def __init__(self, pretrained=1):
+        super(OSVOS_VGG, self).__init__()
+        lay_list, in_channels = _LAY_LIST, _IN_CHANNELS
+        stages = modules.ModuleList()
+        side_prep = modules.ModuleList()
+        score_dsn = modules.ModuleList()
+        upscale = modules.ModuleList()
+        upscale_ = modules.ModuleList()
+        for i in range(0, len(lay_list)):
+            stages.append(self._make_layers_osvos(lay_list[i], in_channels[i]))
+            if i > 0:
+                side_prep.append(nn.Conv2d(lay_list[i][-1], 16, kernel_size=3, padding=1))
+                score_dsn.append(nn.Conv2d(16, 1, kernel_size=1, padding=0))
+                upscale_.append(nn.ConvTranspose2d(1, 1, kernel_size=2 ** (1 + i), stride=2 ** i, bias=False))
+                upscale.append(nn.ConvTranspose2d(16, 16, kernel_size=2 ** (1 + i), stride=2 ** i, bias=False))
+        # attribute order fixes the state_dict key order (reference osvos_vgg.py:50-56)
+        self.upscale = upscale
+        self.upscale_ = upscale_
+        self.stages = stages
+        self.side_prep = side_prep
+        self.score_dsn = score_dsn
+        self.fuse = nn.Conv2d(64, 1, kernel_size=1, padding=0)
+        self._initialize_weights(pretrained)
+
+        self.precision = os.environ.get("FOSVOS_PRECISION", "bf16")
+        self._packed: Dict[int, _PackedConv] = {}
+        self._side_key = None
+        self._side_params: Optional[torch.Tensor] = None
+        self._side_general = False
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def _make_layers_osvos(cfg, in_channels):
+        layers = []
+        for v in cfg:
+            if v == 'M':
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2, ceil_mode=True))
+            else:
+                layers.extend([nn.Conv2d(in_channels, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)])
+                in_channels = v
+        return nn.Sequential(*layers)
+
+    def _initialize_weights(self, pretrained):
+        # reference osvos_vgg.py:97-116
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data.normal_(0, 0.001)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.ConvTranspose2d):
+                m.weight.data.zero_()
+                m.weight.data = interp_surgery(m)
+        if pretrained == 1:
+            self._load_from_pytorch()
+        elif pretrained == 2:
+            self._load_from_caffe()
+
+    def _load_from_pytorch(self) -> None:
+        # reference osvos_vgg.py:118-129: copy torchvision VGG-16 conv weights in order
+        from copy import deepcopy
+        from torchvision.models import vgg16
+        _vgg = vgg16(pretrained=True)
+        inds = [i for i in range(len(_vgg.features)) if isinstance(_vgg.features[i], nn.Conv2d)]
+        k = 0
+        for i in range(len(self.stages)):
+            for j in range(len(self.stages[i])):
+                if isinstance(self.stages[i][j], nn.Conv2d):
+                    self.stages[i][j].weight = deepcopy(_vgg.features[inds[k]].weight)
+                    self.stages[i][j].bias = deepcopy(_vgg.features[inds[k]].bias)
+                    k += 1
+
+    def _load_from_caffe(self, models_dir: Optional[str] = None) -> None:
+        # reference osvos_vgg.py:139-153 (path from config.mypath there; FOSVOS_MODELS_DIR here)
+        import scipy.io
+        models_dir = models_dir or os.environ.get("FOSVOS_MODELS_DIR", ".")
+        caffe_weights = scipy.io.loadmat(os.path.join(models_dir, 'vgg_hed_caffe.mat'))
+        caffe_ind = 0
+        for ind, layer in enumerate(self.stages.parameters()):
+            if ind % 2 == 0:
+                c_w = torch.from_numpy(caffe_weights['weights'][0][caffe_ind].transpose())
+                assert layer.data.shape == c_w.shape
+                layer.data = c_w
+            else:
+                c_b = torch.from_numpy(caffe_weights['biases'][0][caffe_ind][:, 0])
+                assert layer.data.shape == c_b.shape
+                layer.data = c_b
+                caffe_ind += 1
+
+    # ------------------------------------------------------------------ derived caches
+    def _stage_convs(self) -> List[List[nn.Conv2d]]:
+        return [[m for m in st if isinstance(m, nn.Conv2d)] for st in self.stages]
+
+    def _impl(self) -> str:
+        if self.precision == "bf16":
+            return "tc"
+        if self.precision in ("fp32", "bf16_simt"):
+            return "simt"
+        raise RuntimeError(f"fosvos_b200: unknown precision mode '{self.precision}'")
+
+    def _packed_for(self, conv: nn.Conv2d, need_dgrad: bool) -> _PackedConv:
+        pc = self._packed.setdefault(id(conv), _PackedConv())
+        b = conv.bias
+        key = (conv.weight.data_ptr(), conv.weight._version, None if b is None else (b.data_ptr(), b._version),
+               self.precision, tuple(conv.weight.shape))
+        if pc.key != key:
+            pc.w_fwd = pc.w_dgrad = pc.bias = None
+            pc.key = key
+        dt = _act_dtype(self.precision)
+        tc = self._impl() == "tc"
+        if pc.w_fwd is None:
+            pc.w_fwd = ops.pack_weight(conv.weight, L.W_TC_FWD if tc else L.W_SIMT_FWD, dt)
+            pc.bias = ops.pad_bias(b, conv.out_channels, conv.weight.device)
+        if need_dgrad and pc.w_dgrad is None:
+            pc.w_dgrad = ops.pack_weight(conv.weight, L.W_TC_DGRAD if tc else L.W_SIMT_DGRAD, dt)
+        return pc
+
+    def invalidate_packed(self) -> None:
+        """Drop the packed copies (call after mutating parameters without bumping ``_version``)."""
+        self._packed.clear()
+        self._side_key = None
+
+    def _side(self) -> torch.Tensor:
+        ps = [m.weight for m in self.upscale] + [m.weight for m in self.upscale_] + \
+             [m.weight for m in self.score_dsn] + [m.bias for m in self.score_dsn] + [self.fuse.weight, self.fuse.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._side_key:
+            up_key = key[:4]
+            if self._side_key is None or self._side_key[:4] != up_key:
+                # structure check of the up-sampling weights (one sync, only when they change)
+                self._side_general = bool(ops.side_check_diagonal([m.weight for m in self.upscale]).item() != 0)
+            self._side_params = ops.side_params_prepare([m.weight for m in self.upscale], [m.weight for m in self.upscale_],
+                                                        [m.weight for m in self.score_dsn], [m.bias for m in self.score_dsn],
+                                                        self.fuse.weight, self.fuse.bias, out=self._side_params)
+            self._side_key = key
+        return self._side_params
+
+    # ------------------------------------------------------------------ the path
+    def _run_forward(self, x: torch.Tensor, save: bool, want_prob: bool = False, want_mask: bool = False):
+        """NHWC pipeline.  Returns (outs, prob, mask, saved) ; saved holds what backward needs."""
+        L.require_device(x.device)
+        if x.dim() != 4 or x.shape[1] != self.stages[0][0].in_channels:
+            raise RuntimeError(f"OSVOS_VGG.forward expects (N,{self.stages[0][0].in_channels},H,W), got {tuple(x.shape)}")
+        H, W = int(x.shape[-2]), int(x.shape[-1])
+        dt = _act_dtype(self.precision)
+        impl = self._impl()
+        a = ops.nchw_to_nhwc(x.float(), dt)
+        conv_in: List[torch.Tensor] = []        # input activation of every stage conv, in order
+        conv_out: List[torch.Tensor] = []
+        pool_in: List[Optional[torch.Tensor]] = []
+        stage_out: List[torch.Tensor] = []
+        sps: List[torch.Tensor] = []
+        for si, convs in enumerate(self._stage_convs()):
+            if si > 0:
+                pool_in.append(a)
+                a = ops.maxpool2x2(a)
+            for conv in convs:
+                pc = self._packed_for(conv, need_dgrad=save)
+                conv_in.append(a)
+                a = ops.conv3x3(a, pc.w_fwd, pc.bias, ops.pad8(conv.out_channels), L.CONV_BIAS | L.CONV_RELU, impl=impl)
+                conv_out.append(a)
+            stage_out.append(a)
+            if si > 0:
+                sp_conv = self.side_prep[si - 1]
+                pc = self._packed_for(sp_conv, need_dgrad=save)
+                sps.append(ops.conv3x3(a, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, impl=impl))
+        params = self._side()
+        outs, prob, mask = ops.side_fwd(sps, params, H, W, general=self._side_general, want_prob=want_prob, want_mask=want_mask)
+        saved = None
+        if save:
+            saved = dict(conv_in=conv_in, conv_out=conv_out, pool_in=pool_in, stage_out=stage_out, sps=sps, H=H, W=W,
+                         params=params)
+        return outs, prob, mask, saved
+
+    def _run_backward(self, saved, douts: Sequence[Optional[torch.Tensor]], grads: Dict[str, torch.Tensor]) -> None:
+        """Accumulate (+=) parameter gradients into ``grads`` (name -> fp32 tensor, reference layout)."""
+        if self._side_general:
+            raise RuntimeError("fosvos_b200: backward through non-diagonal `upscale` weights is not supported "
+                               "(the reference keeps them fixed with lr=0, network_provider.py:154-155)")
+        impl = self._impl()
+        H, W = saved["H"], saved["W"]
+        sps = saved["sps"]
+        if douts[4] is None:
+            douts = list(douts)
+            douts[4] = torch.zeros_like(next(d for d in douts if d is not None))
+        g = lambda k: grads.get(k)  # noqa: E731
+        dsp = ops.side_bwd(sps, saved["params"], douts, H, W, g("fuse.weight"), g("fuse.bias"),
+                           [g(f"score_dsn.{i}.weight") for i in range(4)], [g(f"score_dsn.{i}.bias") for i in range(4)])
+        convs = self._stage_convs()
+        names = [[f"stages.{si}.{mi}" for mi, m in enumerate(st) if isinstance(m, nn.Conv2d)] for si, st in enumerate(self.stages)]
+        # flat index of the first conv of each stage
+        first = [0]
+        for c in convs[:-1]:
+            first.append(first[-1] + len(c))
+        dA: Optional[torch.Tensor] = None          # gradient w.r.t. the current stage's output (pre-activation-masked)
+        for si in range(4, -1, -1):
+            a_out = saved["stage_out"][si]
+            if si > 0:
+                spc = self.side_prep[si - 1]
+                pc = self._packed_for(spc, need_dgrad=True)
+                ops.conv3x3_wgrad(a_out, dsp[si - 1], grads[f"side_prep.{si - 1}.weight"], g(f"side_prep.{si - 1}.bias"))
+                flags = L.CONV_MASK | (L.CONV_ACCUMULATE if dA is not None else 0)
+                dA = ops.conv3x3(dsp[si - 1], pc.w_dgrad, None, a_out.shape[3], flags, mask=a_out, out=dA, impl=impl)
+            dz = dA
+            for j in range(len(convs[si]) - 1, -1, -1):
+                conv = convs[si][j]
+                k = first[si] + j
+                x_in = saved["conv_in"][k]
+                name = names[si][j]
+                ops.conv3x3_wgrad(x_in, dz, grads[name + ".weight"], g(name + ".bias"))
+                if si == 0 and j == 0:
+                    break
+                pc = self._packed_for(conv, need_dgrad=True)
+                # dX masked by (x_in > 0): x_in is the previous layer's post-ReLU output (or its pooled copy)
+                dz = ops.conv3x3(dz, pc.w_dgrad, None, x_in.shape[3], L.CONV_MASK, mask=x_in, impl=impl)
+            if si > 0:
+                dA = ops.maxpool2x2_bwd(saved["pool_in"][si - 1], dz)
+
+    def _grad_names(self) -> List[str]:
+        return [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("upscale")]
+
+    def forward(self, x):
+        params = dict(self.named_parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params.values()):
+            names = self._grad_names()
+            outs = _OSVOSFunction.apply(self, x, names, *[params[n] for n in names])
+            return list(outs)
+        outs, _, _, _ = self._run_forward(x, save=False)
+        return outs
+
+    @torch.no_grad()
+    def predict(self, x):
+        """Inference with the consumer-side post-processing fused in: returns
+        (outs, prob, mask): sigmoid (util/experiment_helper.py:57) and the 0.5 threshold
+        (run_webcam.py:92-93) of the fused map come out of the same kernel."""
+        outs, prob, mask, _ = self._run_forward(x, save=False, want_prob=True, want_mask=True)
+        return outs, prob, mask
+
+
+class _OSVOSFunction(torch.autograd.Function):
+    """Autograd bridge: the whole network is one node whose backward runs our kernels.
+    Gradients w.r.t. the input frame and the (lr=0) up-sampling weights are not produced."""
+
+    @staticmethod
+    def forward(ctx, net: OSVOS_VGG, x, names, *params):
+        outs, _, _, saved = net._run_forward(x.detach(), save=True)
+        ctx.net, ctx.saved, ctx.names = net, saved, names
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.device = x.device
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        grads = {n: torch.zeros(s, dtype=torch.float32, device=ctx.device) for n, s in zip(ctx.names, ctx.shapes)}
+        ctx.net._run_backward(ctx.saved, [None if d is None else d.contiguous() for d in douts], grads)
+        ctx.saved = None
+        return (None, None, None) + tuple(grads[n] for n in ctx.names)

@@ -1,0 +1,254 @@
+"""Tensor-level wrappers around the C ABI (one function per entry point).
+
+Every function takes/returns CUDA tensors, enqueues on the current stream and never
+synchronises.  Activations are NHWC (``(N,H,W,Cp)``, ``Cp % 8 == 0``) in fp32 or bf16.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, cp: Optional[int] = None) -> torch.Tensor:
+    L.require_device(x.device)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    cp = pad8(c) if cp is None else cp
+    y = torch.empty((n, h, w, cp), dtype=dtype, device=x.device)
+    L.check(L.lib().fosvos_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), n, c, h, w, cp, L.dtype_code(dtype), L.stream()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    L.require_device(x.device)
+    n, h, w, cp = x.shape
+    c = cp if c is None else c
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(L.lib().fosvos_nhwc_to_nchw(x.data_ptr(), y.data_ptr(), n, c, h, w, cp, L.dtype_code(x.dtype), L.stream()), "nhwc_to_nchw")
+    return y
+
+
+def pack_weight(w: torch.Tensor, layout: int, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """OIHW fp32 (Cout,Cin,3,3) -> packed kernel layout (see fosvos_wlayout)."""
+    L.require_device(w.device)
+    assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
+    w = w.detach().contiguous()
+    cout, cin = w.shape[0], w.shape[1]
+    coutp, cinp = pad8(cout), pad8(cin)
+    n = L.lib().fosvos_packed_weight_elems(coutp, cinp, layout)
+    if out is None:
+        out = torch.empty(n, dtype=dtype, device=w.device)
+    assert out.numel() == n and out.dtype == dtype
+    L.check(L.lib().fosvos_pack_conv3x3_weight(w.data_ptr(), out.data_ptr(), cout, cin, coutp, cinp, layout,
+                                               L.dtype_code(dtype), L.stream()), "pack_conv3x3_weight")
+    return out
+
+
+def pad_bias(b: Optional[torch.Tensor], c: int, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    cp = pad8(c)
+    if out is None:
+        out = torch.empty(cp, dtype=torch.float32, device=device)
+    L.check(L.lib().fosvos_pad_bias(L.ptr(None if b is None else b.detach()), out.data_ptr(), c, cp, L.stream()), "pad_bias")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout_p: int, flags: int,
+            mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, impl: str = "tc") -> torch.Tensor:
+    """3x3/s1/p1 convolution over NHWC activations.  impl: 'tc' (tcgen05, bf16) or 'simt'."""
+    L.require_device(x.device)
+    n, h, w, cin_p = x.shape
+    if out is None:
+        assert not (flags & L.CONV_ACCUMULATE)
+        out = torch.empty((n, h, w, cout_p), dtype=x.dtype, device=x.device)
+    assert out.shape == (n, h, w, cout_p) and out.dtype == x.dtype and x.is_contiguous() and out.is_contiguous()
+    if mask is not None:
+        assert mask.shape == out.shape and mask.dtype == x.dtype and mask.is_contiguous()
+    if impl == "tc":
+        assert x.dtype == torch.bfloat16, "the tcgen05 path computes in bf16"
+        rc = L.lib().fosvos_conv3x3_tc(x.data_ptr(), w_packed.data_ptr(), L.ptr(bias), L.ptr(mask), out.data_ptr(),
+                                       n, h, w, cin_p, cout_p, flags, L.stream())
+    elif impl == "simt":
+        rc = L.lib().fosvos_conv3x3_simt(x.data_ptr(), w_packed.data_ptr(), L.ptr(bias), L.ptr(mask), out.data_ptr(),
+                                         n, h, w, cin_p, cout_p, flags, L.dtype_code(x.dtype), L.stream())
+    else:
+        raise ValueError(impl)
+    L.check(rc, f"conv3x3_{impl}")
+    return out
+
+
+def conv3x3_wgrad(x: torch.Tensor, dz: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    """dw (OIHW fp32) += x (*) dz ; db += sum dz.  Accumulates in place."""
+    L.require_device(x.device)
+    n, h, w, cin_p = x.shape
+    cout_p = dz.shape[3]
+    cout, cin = dw.shape[0], dw.shape[1]
+    assert dz.shape[:3] == x.shape[:3] and dw.dtype == torch.float32 and dw.is_contiguous()
+    assert x.dtype == dz.dtype and x.is_contiguous() and dz.is_contiguous()
+    L.check(L.lib().fosvos_conv3x3_wgrad_simt(x.data_ptr(), dz.data_ptr(), dw.data_ptr(), L.ptr(db), n, h, w, cin_p, cout_p,
+                                              cin, cout, L.dtype_code(x.dtype), L.stream()), "conv3x3_wgrad_simt")
+
+
+def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
+    L.require_device(x.device)
+    n, h, w, c = x.shape
+    y = torch.empty((n, (h + 1) // 2, (w + 1) // 2, c), dtype=x.dtype, device=x.device)
+    L.check(L.lib().fosvos_maxpool2x2_fwd(x.data_ptr(), y.data_ptr(), n, h, w, c, L.dtype_code(x.dtype), L.stream()), "maxpool2x2_fwd")
+    return y
+
+
+def maxpool2x2_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    L.require_device(x.device)
+    n, h, w, c = x.shape
+    assert dy.shape == (n, (h + 1) // 2, (w + 1) // 2, c) and dy.dtype == x.dtype
+    dx = torch.empty_like(x)
+    L.check(L.lib().fosvos_maxpool2x2_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, c, L.dtype_code(x.dtype), L.stream()), "maxpool2x2_bwd")
+    return dx
+
+
+# ---- side-output chain -----------------------------------------------------------------------
+def side_params_prepare(upscale_w: Sequence[torch.Tensor], upscale1_w: Sequence[torch.Tensor], score_w: Sequence[torch.Tensor],
+                        score_b: Sequence[torch.Tensor], fuse_w: torch.Tensor, fuse_b: torch.Tensor,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = fuse_w.device
+    L.require_device(dev)
+    if out is None:
+        out = torch.empty(L.lib().fosvos_side_params_bytes() // 4, dtype=torch.float32, device=dev)
+    for i in range(4):
+        k = 4 << i
+        assert tuple(upscale_w[i].shape) == (16, 16, k, k) and tuple(upscale1_w[i].shape) == (1, 1, k, k)
+    keep = [t.detach().contiguous() for t in list(upscale_w) + list(upscale1_w) + list(score_w) + list(score_b)]
+    fw, fb = fuse_w.detach().contiguous(), fuse_b.detach().contiguous()
+    L.check(L.lib().fosvos_side_prepare(L.ptr_array(keep[0:4]), L.ptr_array(keep[4:8]), L.ptr_array(keep[8:12]),
+                                        L.ptr_array(keep[12:16]), fw.data_ptr(), fb.data_ptr(), out.data_ptr(), L.stream()),
+            "side_prepare")
+    return out
+
+
+def side_check_diagonal(upscale_w: Sequence[torch.Tensor]) -> torch.Tensor:
+    """int32 device scalar: number of elements violating the diagonal/shared-kernel structure."""
+    keep = [t.detach().contiguous() for t in upscale_w]
+    flag = torch.empty(1, dtype=torch.int32, device=keep[0].device)
+    L.check(L.lib().fosvos_side_check_diagonal(L.ptr_array(keep), flag.data_ptr(), L.stream()), "side_check_diagonal")
+    return flag
+
+
+def side_fwd(sp: Sequence[torch.Tensor], params: torch.Tensor, H: int, W: int, general: bool = False,
+             want_prob: bool = False, want_mask: bool = False):
+    """-> ([side0..3, fused] each (N,1,H,W) fp32, prob or None, mask or None)"""
+    dev = params.device
+    L.require_device(dev)
+    n = sp[0].shape[0]
+    hs = [int(t.shape[1]) for t in sp]
+    ws = [int(t.shape[2]) for t in sp]
+    for t in sp:
+        assert t.shape[3] == 16 and t.is_contiguous() and t.dtype == sp[0].dtype
+    outs = [torch.empty((n, 1, H, W), dtype=torch.float32, device=dev) for _ in range(5)]
+    prob = torch.empty((n, 1, H, W), dtype=torch.float32, device=dev) if want_prob else None
+    mask = torch.empty((n, 1, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+    ha, wa = L.int_array(hs), L.int_array(ws)
+    wsb = L.lib().fosvos_side_workspace_bytes(ha, wa, n)
+    workspace = None if general else torch.empty(wsb, dtype=torch.uint8, device=dev)
+    L.check(L.lib().fosvos_side_fwd(L.ptr_array(sp), ha, wa, params.data_ptr(), L.ptr_array(outs), L.ptr(prob), L.ptr(mask),
+                                    L.ptr(workspace), int(general), n, H, W, L.dtype_code(sp[0].dtype), L.stream()), "side_fwd")
+    return outs, prob, mask
+
+
+def side_bwd(sp: Sequence[torch.Tensor], params: torch.Tensor, dout: Sequence[Optional[torch.Tensor]], H: int, W: int,
+             d_fuse_w: Optional[torch.Tensor], d_fuse_b: Optional[torch.Tensor],
+             d_score_w: Optional[Sequence[Optional[torch.Tensor]]], d_score_b: Optional[Sequence[Optional[torch.Tensor]]]) -> List[torch.Tensor]:
+    """Returns dsp[0..3]; accumulates into the given parameter-gradient tensors."""
+    L.require_device(params.device)
+    n = sp[0].shape[0]
+    hs = [int(t.shape[1]) for t in sp]
+    ws = [int(t.shape[2]) for t in sp]
+    assert dout[4] is not None
+    douts = [None if d is None else d.contiguous() for d in dout]
+    for d in douts:
+        assert d is None or (d.dtype == torch.float32 and d.numel() == n * H * W)
+    dsp = [torch.empty_like(t) for t in sp]
+    L.check(L.lib().fosvos_side_bwd(L.ptr_array(sp), L.int_array(hs), L.int_array(ws), params.data_ptr(), L.ptr_array(douts),
+                                    L.ptr_array(dsp), L.ptr(d_fuse_w), L.ptr(d_fuse_b),
+                                    L.ptr_array(d_score_w) if d_score_w is not None else None,
+                                    L.ptr_array(d_score_b) if d_score_b is not None else None,
+                                    n, H, W, L.dtype_code(sp[0].dtype), L.stream()), "side_bwd")
+    return dsp
+
+
+# ---- loss -----------------------------------------------------------------------------------
+def bal_loss_fwd(output: torch.Tensor, label: torch.Tensor, size_average: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (loss 0-dim fp32, stats (8,) float64)"""
+    L.require_device(output.device)
+    assert output.dtype == torch.float32 and label.dtype == torch.float32 and output.numel() == label.numel()
+    output, label = output.contiguous(), label.contiguous()
+    stats = torch.empty(8, dtype=torch.float64, device=output.device)
+    loss = torch.empty((), dtype=torch.float32, device=output.device)
+    L.check(L.lib().fosvos_bal_loss_fwd(output.data_ptr(), label.data_ptr(), output.numel(), int(size_average),
+                                        stats.data_ptr(), loss.data_ptr(), L.stream()), "bal_loss_fwd")
+    return loss, stats
+
+
+def bal_loss_bwd(output: torch.Tensor, label: torch.Tensor, size_average: bool, stats: torch.Tensor,
+                 grad_out: Optional[torch.Tensor], grad_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    output, label = output.contiguous(), label.contiguous()
+    dx = torch.empty_like(output) if out is None else out
+    if grad_out is not None:
+        grad_out = grad_out.to(torch.float32).contiguous()
+    L.check(L.lib().fosvos_bal_loss_bwd(output.data_ptr(), label.data_ptr(), output.numel(), int(size_average),
+                                        stats.data_ptr(), L.ptr(grad_out), float(grad_scale), dx.data_ptr(), L.stream()),
+            "bal_loss_bwd")
+    return dx
+
+
+# ---- optimizer ------------------------------------------------------------------------------
+SGD_ENTRY = np.dtype([("p", np.uint64), ("g", np.uint64), ("buf", np.uint64), ("n", np.int64), ("lr", np.float32),
+                      ("wd", np.float32)])
+
+
+def sgd_table(entries: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, float, float]], device) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """entries: (param, grad, momentum_buffer, lr, weight_decay) -> (table, chunk_prefix, n_chunks) on device."""
+    chunk = L.lib().fosvos_sgd_chunk_elems()
+    tab = np.zeros(len(entries), dtype=SGD_ENTRY)
+    prefix = np.zeros(len(entries) + 1, dtype=np.int64)
+    for i, (p, g, b, lr, wd) in enumerate(entries):
+        assert p.dtype == g.dtype == b.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous() and b.is_contiguous()
+        tab[i] = (p.data_ptr(), g.data_ptr(), b.data_ptr(), p.numel(), lr, wd)
+        prefix[i + 1] = prefix[i] + (p.numel() + chunk - 1) // chunk
+    assert SGD_ENTRY.itemsize == 40
+    t = torch.from_numpy(tab.view(np.uint8).copy()).to(device)
+    pf = torch.from_numpy(prefix).to(device)
+    return t, pf, int(prefix[-1])
+
+
+def sgd_step(table: torch.Tensor, prefix: torch.Tensor, n_tensors: int, n_chunks: int, momentum: float, zero_grad: bool) -> None:
+    L.check(L.lib().fosvos_sgd_step(table.data_ptr(), n_tensors, prefix.data_ptr(), n_chunks, float(momentum), int(zero_grad),
+                                    L.stream()), "sgd_step")
+
+
+# ---- mask egress ------------------------------------------------------------------------------
+def sigmoid_threshold(logits: torch.Tensor, want_prob: bool = True, want_mask: bool = True):
+    L.require_device(logits.device)
+    logits = logits.contiguous()
+    prob = torch.empty_like(logits) if want_prob else None
+    mask = torch.empty(logits.shape, dtype=torch.uint8, device=logits.device) if want_mask else None
+    L.check(L.lib().fosvos_sigmoid_threshold(logits.data_ptr(), L.ptr(prob), L.ptr(mask), logits.numel(), L.stream()), "sigmoid_threshold")
+    return prob, mask
+
+
+def mask_iou(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a, b: uint8 {0,1} masks (F, ...) -> int64 (F, 2): intersection and union pixel counts per frame."""
+    L.require_device(a.device)
+    assert a.dtype == torch.uint8 and b.dtype == torch.uint8 and a.shape == b.shape
+    a, b = a.contiguous(), b.contiguous()
+    f = a.shape[0]
+    counts = torch.empty((f, 2), dtype=torch.int64, device=a.device)
+    L.check(L.lib().fosvos_mask_iou(a.data_ptr(), b.data_ptr(), a.numel() // f, f, counts.data_ptr(), L.stream()), "mask_iou")
+    return counts

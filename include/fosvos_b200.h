@@ -1,0 +1,215 @@
+/*
+ * fosvos_b200.h -- C ABI of libfosvos_sm100.so
+ *
+ * The drop-in boundary of the B200-native OSVOS VGG-16 hot path.  The reference
+ * (klausondrag/FOSVOS) has no FFI of its own: its arithmetic goes through
+ * PyTorch library calls.  Each entry point below replaces one such call group
+ * on the path named by BASELINE.json; the reference call site it replaces is
+ * cited as file:line into /root/reference/src.  INTEGRATION.md shows the
+ * ctypes binding the reference's maintainers would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every pointer is a DEVICE pointer unless named host_*
+ *   - the caller owns all memory (incl. workspaces); pointers are borrowed for
+ *     the duration of the work enqueued on `stream` (a cudaStream_t)
+ *   - nothing synchronises; every call is CUDA-graph capturable
+ *   - return 0 on success, a negative fosvos_status otherwise; no exceptions
+ *     cross the ABI; fosvos_last_error() gives a human-readable reason
+ *   - activations inside the path are NHWC ("pixel-major"): element (n,y,x,c)
+ *     lives at ((n*H + y)*W + x)*C + c, C a multiple of 8; dtype is
+ *     FOSVOS_F32 or FOSVOS_BF16.  Tensors at the module boundary keep the
+ *     reference's NCHW fp32 layout (input frame, the five logit maps).
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every
+ *     compute entry point returns FOSVOS_ERR_NO_DEVICE / FOSVOS_ERR_ARCH.
+ */
+#ifndef FOSVOS_B200_H_
+#define FOSVOS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fosvos_stream_t; /* cudaStream_t */
+
+enum fosvos_status {
+  FOSVOS_OK = 0,
+  FOSVOS_ERR_BAD_ARG = -1,   /* shape / alignment / enum out of range            */
+  FOSVOS_ERR_ARCH = -2,      /* device is not compute capability 10.x             */
+  FOSVOS_ERR_NO_DEVICE = -3, /* no CUDA device / driver                            */
+  FOSVOS_ERR_LAUNCH = -4,    /* cudaGetLastError() after a launch                  */
+  FOSVOS_ERR_DRIVER = -5,    /* tensor-map encode or other driver-API failure      */
+  FOSVOS_ERR_UNSUPPORTED = -6
+};
+
+enum fosvos_dtype { FOSVOS_F32 = 0, FOSVOS_BF16 = 1 };
+
+/* epilogue flags of the 3x3 convolution kernels */
+enum fosvos_conv_flags {
+  FOSVOS_CONV_BIAS = 1,       /* add bias[cout]                                           */
+  FOSVOS_CONV_RELU = 2,       /* max(.,0): nn.ReLU(inplace=True), osvos_vgg.py:93         */
+  FOSVOS_CONV_MASK = 4,       /* multiply by (mask[n,y,x,cout] > 0): ReLU backward        */
+  FOSVOS_CONV_ACCUMULATE = 8  /* y += result instead of y = result (gradient fan-in)      */
+};
+
+/* packed layouts of a 3x3 conv weight (source is always OIHW fp32, the
+ * reference state_dict layout, osvos_vgg.py:92) */
+enum fosvos_wlayout {
+  FOSVOS_W_SIMT_FWD = 0,   /* [tap][cin][cout]                       (direct kernels)      */
+  FOSVOS_W_SIMT_DGRAD = 1, /* [tap'][cout][cin], tap' = 8 - tap      (direct kernels)      */
+  FOSVOS_W_TC_FWD = 2,     /* [cout][tap][cin_pad]   K-major bf16    (tcgen05 kernels)     */
+  FOSVOS_W_TC_DGRAD = 3    /* [cin][tap'][cout_pad]  K-major bf16    (tcgen05 kernels)     */
+};
+
+/* ---- library / device ------------------------------------------------------------ */
+int fosvos_abi_version(void);                 /* bumps when any signature changes      */
+const char* fosvos_last_error(void);          /* thread-local, never NULL              */
+int fosvos_device_check(int device);          /* FOSVOS_OK iff `device` is sm_100      */
+int fosvos_num_sms(int device);               /* >0, or a negative status              */
+
+/* ---- frame ingest ------------------------------------------------------------------
+ * NCHW fp32 frame (N,C,H,W) -> NHWC activations (N,H,W,Cp), channels >= C zeroed.
+ * Replaces the implicit layout of the tensor handed to net.forward
+ * (train_online.py:79, util/experiment_helper.py:46). */
+int fosvos_nchw_to_nhwc(const float* x_nchw, void* y_nhwc, int N, int C, int H, int W, int Cp,
+                        int dtype, fosvos_stream_t stream);
+/* NHWC activations -> NCHW fp32 (introspection path: per-conv outputs for hooks,
+ * prune.py:96-103). */
+int fosvos_nhwc_to_nchw(const void* x_nhwc, float* y_nchw, int N, int C, int H, int W, int Cp,
+                        int dtype, fosvos_stream_t stream);
+
+/* ---- weights -----------------------------------------------------------------------
+ * Repack one OIHW fp32 3x3 weight (Cout,Cin,3,3) into a kernel layout (derived cache; never
+ * serialised -- the state_dict keeps the reference layout, osvos_vgg.py:50-56).
+ * CoutP/CinP are the padded channel counts (multiples of 8) of the NHWC activations the
+ * kernels see; entries outside the logical weight are zero, so pruned networks with arbitrary
+ * widths (prune.py:490-514) run on the same kernels.  The TC layouts additionally pad their
+ * contiguous (GEMM-K) channel dimension to a multiple of 64.
+ * fosvos_packed_weight_elems returns the element count of the packed buffer.
+ * fosvos_pad_bias copies bias (or zeros if NULL: pruned convs have bias=False, prune.py:500)
+ * into a CoutP-long fp32 vector. */
+long long fosvos_packed_weight_elems(int CoutP, int CinP, int layout);
+int fosvos_pack_conv3x3_weight(const float* w_oihw, void* w_packed, int Cout, int Cin, int CoutP,
+                               int CinP, int layout, int dtype, fosvos_stream_t stream);
+int fosvos_pad_bias(const float* bias, float* bias_padded, int C, int Cp, fosvos_stream_t stream);
+
+/* ---- 3x3 convolution, stride 1, pad 1 (nn.Conv2d, osvos_vgg.py:42,92) --------------
+ * y[n,y,x,co] = epilogue( sum_{tap,ci} x[n,y+r-1,x+s-1,ci] * w[co,ci,r,s] )
+ * x: (N,H,W,Cin) NHWC, y: (N,H,W,Cout) NHWC, both `dtype`; bias fp32 or NULL;
+ * mask: (N,H,W,Cout) NHWC `dtype` or NULL (FOSVOS_CONV_MASK).
+ * The same entry points serve the data gradient: pass the *_DGRAD packed
+ * weight, Cin<->Cout swapped, flags = MASK (+ACCUMULATE).
+ *   _simt : direct fp32-accumulate kernel, w_packed in FOSVOS_W_SIMT_* layout, `dtype` elements
+ *   _tc   : tcgen05/TMEM implicit GEMM fed by TMA, bf16 only, FOSVOS_W_TC_* layout */
+int fosvos_conv3x3_simt(const void* x, const void* w_packed, const float* bias, const void* mask,
+                        void* y, int N, int H, int W, int Cin, int Cout, int flags, int dtype,
+                        fosvos_stream_t stream);
+int fosvos_conv3x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
+                      void* y, int N, int H, int W, int Cin, int Cout, int flags,
+                      fosvos_stream_t stream);
+
+/* weight + bias gradient of the same convolution (autograd convolution_backward,
+ * train_online.py:93):  dw[co,ci,r,s] += sum_p x[p+tap,ci] * dz[p,co];  db[co] += sum_p dz[p,co]
+ * x: (N,H,W,CinP), dz: (N,H,W,CoutP) NHWC; dw: OIHW fp32 (Cout,Cin,3,3) -- the parameter's
+ * .grad, accumulated across micro-steps; db (Cout) may be NULL. */
+int fosvos_conv3x3_wgrad_simt(const void* x, const void* dz, float* dw_oihw, float* db, int N, int H,
+                              int W, int CinP, int CoutP, int Cin, int Cout, int dtype,
+                              fosvos_stream_t stream);
+
+/* ---- 2x2 / stride-2 max pooling, ceil_mode=True (nn.MaxPool2d, osvos_vgg.py:90) ---- */
+int fosvos_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype,
+                          fosvos_stream_t stream);
+/* dx = dy routed to the first maximum of each window in (row, col) scan order, zero
+ * elsewhere (what autograd's max_pool2d_with_indices backward does). */
+int fosvos_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C,
+                          int dtype, fosvos_stream_t stream);
+
+/* ---- side-output chain (osvos_vgg.py:69-82) -------------------------------------------
+ * score_dsn 1x1 (:75) -> upscale_ ConvT (:76) -> crop (:77) for the four side maps, and
+ * upscale ConvT (:71) -> crop (:72) -> cat (:80) -> fuse 1x1 (:81) for the fused map, plus the
+ * consumer's sigmoid (util/experiment_helper.py:57) and 0.5 threshold (run_webcam.py:92-93).
+ *
+ * fosvos_side_params: device-resident parameter block, built by fosvos_side_prepare from the
+ * reference-layout weights.  It holds, for each stage i=0..3 (stride s=2^(i+1), k=2s):
+ *   sw[16], sb        score_dsn[i].weight/.bias
+ *   g_[k*k]           upscale_[i].weight (1,1,k,k)
+ *   G[k*k*16]         effective fused kernel  G[ky][kx][c] = sum_co fuse.w[16i+co] * upscale[i].w[c,co,ky,kx]
+ * and fuse.bias.  This is exact for ANY upscale weights (no diagonality assumption).
+ * fosvos_side_params_bytes() gives the block size. */
+size_t fosvos_side_params_bytes(void);
+int fosvos_side_prepare(const float* const* upscale_w /*4: (16,16,k,k)*/,
+                        const float* const* upscale1_w /*4: (1,1,k,k)*/,
+                        const float* const* score_w /*4: (1,16,1,1)*/,
+                        const float* const* score_b /*4: (1)*/, const float* fuse_w /*(1,64,1,1)*/,
+                        const float* fuse_b /*(1)*/, void* params, fosvos_stream_t stream);
+/* sp[i]: side_prep output of stage i+1, NHWC (N,h_i,w_i,16) `dtype`.  All pointer arrays
+ * (`sp`, `out`, ...) are HOST arrays of device pointers.
+ * out[0..3]: side maps, out[4]: fused map, each NCHW fp32 (N,1,H,W) logits (may not be NULL).
+ * prob (fp32) / mask (uint8) of the fused map: optional, NULL to skip.
+ * general=0: fast path, valid when fosvos_side_check_diagonal reports 0 violations; needs a
+ *            workspace of fosvos_side_workspace_bytes(h,w,N) bytes (low-res head maps).
+ * general=1: exact for arbitrary upscale weights (16x more arithmetic), workspace unused. */
+size_t fosvos_side_workspace_bytes(const int* h /*4*/, const int* w /*4*/, int N);
+int fosvos_side_fwd(const void* const* sp /*4*/, const int* h /*4*/, const int* w /*4*/,
+                    const void* params, float* const* out /*5*/, float* prob, uint8_t* mask,
+                    void* workspace, int general, int N, int H, int W, int dtype,
+                    fosvos_stream_t stream);
+/* Backward of the chain for upscale weights that are diagonal with one shared k x k kernel per
+ * stage (what interp_surgery builds, osvos_layers.py:70-81, and what lr=0 keeps,
+ * network_provider.py:154-155).  dout[4] = d fused (required), dout[0..3] = d side maps or NULL.
+ * Writes dsp[i] (N,h_i,w_i,16) `dtype` and accumulates (+=) into the fp32 parameter gradients
+ * d_fuse_w[64], d_fuse_b[1], d_score_w[i][16], d_score_b[i][1] (NULL to skip). */
+int fosvos_side_bwd(const void* const* sp, const int* h, const int* w, const void* params,
+                    const float* const* dout /*5*/, void* const* dsp /*4*/, float* d_fuse_w,
+                    float* d_fuse_b, float* const* d_score_w, float* const* d_score_b, int N, int H,
+                    int W, int dtype, fosvos_stream_t stream);
+/* Counts the elements of upscale[0..3].weight that break "diagonal with one shared k x k kernel"
+ * (0 = the fast forward path and the backward are valid).  Result: int32 at *violations_dev
+ * (device); no sync. */
+int fosvos_side_check_diagonal(const float* const* upscale_w, int* violations_dev, fosvos_stream_t stream);
+
+/* ---- class-balanced sigmoid cross entropy (layers/osvos_layers.py:17-44) -------------
+ * stats (device, 8 doubles): [0]=#pos labels, [1]=#neg, [2]=sum_{y=1} -lv, [3]=sum_{y=0} -lv,
+ * [4..7] scratch.
+ * loss (device fp32 scalar) = neg/total*stats[2] + pos/total*stats[3], / numel if size_average.
+ * fwd zeroes and fills stats; bwd reads it:  dx = g * w(y) * (sigmoid(x) - y) [/ numel],
+ * g = *grad_out (device fp32 scalar, NULL -> 1) times grad_scale. */
+int fosvos_bal_loss_fwd(const float* output, const float* label, long long numel, int size_average,
+                        double* stats, float* loss, fosvos_stream_t stream);
+int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel, int size_average,
+                        const double* stats, const float* grad_out, float grad_scale, float* dx,
+                        fosvos_stream_t stream);
+
+/* ---- SGD with momentum, multi-tensor (torch.optim.SGD.step, train_online.py:99;
+ *      groups: util/network_provider.py:144-159) ---------------------------------------
+ * One launch updates every tensor:  d = g + wd*p;  buf = mu*buf + d;  p -= lr*buf.
+ * (buf zero-initialised == torch's "buf = d on the first step".)
+ * `table` is a device array of n_tensors fosvos_sgd_entry. zero_grad!=0 also clears g. */
+typedef struct fosvos_sgd_entry {
+  float* p;
+  float* g;
+  float* buf;
+  long long n;
+  float lr;
+  float weight_decay;
+} fosvos_sgd_entry;
+int fosvos_sgd_chunk_elems(void); /* elements per work item: chunk_prefix[t] = sum_{u<t} ceil(n_u / this) */
+int fosvos_sgd_step(const fosvos_sgd_entry* table, int n_tensors, const long long* chunk_prefix,
+                    int n_chunks, float momentum, int zero_grad, fosvos_stream_t stream);
+
+/* ---- mask egress --------------------------------------------------------------------
+ * counts (device, 2 x int64 per frame): intersection and union pixel counts of two uint8
+ * {0,1} masks -- the integers of the DAVIS J (region IoU) measure. Zeroed by the call. */
+int fosvos_mask_iou(const uint8_t* a, const uint8_t* b, long long pixels_per_frame, int n_frames,
+                    long long* counts, fosvos_stream_t stream);
+/* logits fp32 -> probability fp32 and/or uint8 mask (either may be NULL). */
+int fosvos_sigmoid_threshold(const float* logits, float* prob, uint8_t* mask, long long numel,
+                             fosvos_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOSVOS_B200_H_ */

@@ -1,0 +1,353 @@
+"""GPU: every kernel behind the C ABI against the CPU oracle primitives on seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from fosvos_b200 import _lib as L, ops  # noqa: E402
+from oracle import osvos_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(x_nchw, dtype):
+    """CPU NCHW fp32 -> device NHWC (padded to 8 channels)."""
+    return ops.nchw_to_nhwc(x_nchw.to(DEV), dtype)
+
+
+def _nchw(x_nhwc, c):
+    return ops.nhwc_to_nchw(x_nhwc, c).cpu()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1, 3, 5, 7), (2, 16, 9, 4), (1, 20, 3, 3)])
+def test_layout_roundtrip(dtype, shape):
+    x = torch.randn(shape, generator=_gen(0))
+    y = _nhwc(x, dtype)
+    assert y.shape == (shape[0], shape[2], shape[3], ops.pad8(shape[1]))
+    ref = x if dtype == torch.float32 else _bf16r(x)
+    assert torch.equal(y[..., :shape[1]].float().cpu().permute(0, 3, 1, 2), ref)
+    assert (y[..., shape[1]:] == 0).all()
+    assert torch.equal(_nchw(y, shape[1]), ref)
+
+
+@pytest.mark.parametrize("cout,cin", [(64, 3), (16, 128), (20, 12)])
+def test_pack_weight_layouts(cout, cin):
+    w = torch.randn(cout, cin, 3, 3, generator=_gen(1))
+    wd = w.to(DEV)
+    cop, cip = ops.pad8(cout), ops.pad8(cin)
+    wp = torch.zeros(cop, cip, 3, 3)
+    wp[:cout, :cin] = w
+    taps = wp.reshape(cop, cip, 9)
+    simt_f = ops.pack_weight(wd, L.W_SIMT_FWD, torch.float32).cpu().view(9, cip, cop)
+    assert torch.equal(simt_f, taps.permute(2, 1, 0))
+    simt_d = ops.pack_weight(wd, L.W_SIMT_DGRAD, torch.float32).cpu().view(9, cop, cip)
+    assert torch.equal(simt_d, taps.flip(2).permute(2, 0, 1))
+    pad = (cip + 63) // 64 * 64
+    tc_f = ops.pack_weight(wd, L.W_TC_FWD, torch.bfloat16).float().cpu().view(cop, 9, pad)
+    assert torch.equal(tc_f[:, :, :cip], _bf16r(taps.permute(0, 2, 1))) and (tc_f[:, :, cip:] == 0).all()
+    padc = (cop + 63) // 64 * 64
+    tc_d = ops.pack_weight(wd, L.W_TC_DGRAD, torch.bfloat16).float().cpu().view(cip, 9, padc)
+    assert torch.equal(tc_d[:, :, :cop], _bf16r(taps.flip(2).permute(1, 2, 0))) and (tc_d[:, :, cop:] == 0).all()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout
+    (1, 9, 11, 3, 64),
+    (2, 16, 16, 64, 64),
+    (1, 17, 23, 64, 128),
+    (1, 8, 40, 128, 16),
+    (1, 30, 54, 24, 40),
+    (1, 5, 3, 256, 256),
+]
+
+
+def _conv_ref(x, w, b, relu):
+    y = F.conv2d(x.double(), w.double(), None if b is None else b.double(), padding=1)
+    return (F.relu(y) if relu else y).float()
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("mode", ["fp32_simt", "bf16_simt", "bf16_tc"])
+def test_conv3x3_forward(case, mode):
+    n, h, w_, cin, cout = case
+    g = _gen(hash(case) % 1000)
+    x = torch.randn(n, cin, h, w_, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    dt = torch.float32 if mode == "fp32_simt" else torch.bfloat16
+    impl = "tc" if mode == "bf16_tc" else "simt"
+    xd = _nhwc(x, dt)
+    wp = ops.pack_weight(w.to(DEV), L.W_TC_FWD if impl == "tc" else L.W_SIMT_FWD, dt)
+    bp = ops.pad_bias(b.to(DEV), cout, DEV)
+    y = ops.conv3x3(xd, wp, bp, ops.pad8(cout), L.CONV_BIAS | L.CONV_RELU, impl=impl)
+    torch.cuda.synchronize()
+    got = _nchw(y, cout)
+    if dt == torch.float32:
+        ref = _conv_ref(x, w, b, True)
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), float((got - ref).abs().max())
+    else:
+        ref = _conv_ref(_bf16r(x), _bf16r(w), b, True)     # same rounded operands, exact accumulation
+        # one bf16 rounding of the result (2^-9 relative) + fp32 accumulation order
+        assert torch.allclose(got, ref, rtol=2 ** -7, atol=2e-2), float((got - ref).abs().max())
+    assert (y[..., cout:] == 0).all()
+
+
+@pytest.mark.parametrize("impl,dt", [("simt", torch.float32), ("tc", torch.bfloat16)])
+def test_conv3x3_mask_accumulate_dgrad(impl, dt):
+    """The data-gradient use of the kernel: flipped/transposed weights, ReLU mask, += fan-in."""
+    g = _gen(5)
+    n, h, w_, cin, cout = 1, 13, 18, 64, 128
+    x = torch.randn(n, cin, h, w_, generator=g).clamp_min(0)             # post-ReLU activation (has zeros)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+    dz = torch.randn(n, cout, h, w_, generator=g)
+    prev = torch.randn(n, cin, h, w_, generator=g)
+    r = (lambda t: t) if dt == torch.float32 else _bf16r
+    ref = F.conv_transpose2d(r(dz).double(), r(wt).double(), padding=1).float() * (r(x) > 0) + r(prev)
+    wp = ops.pack_weight(wt.to(DEV), L.W_TC_DGRAD if impl == "tc" else L.W_SIMT_DGRAD, dt)
+    out = _nhwc(prev, dt)
+    ops.conv3x3(_nhwc(dz, dt), wp, None, cin, L.CONV_MASK | L.CONV_ACCUMULATE, mask=_nhwc(x, dt), out=out, impl=impl)
+    got = _nchw(out, cin)
+    tol = dict(rtol=1e-4, atol=1e-4) if dt == torch.float32 else dict(rtol=2 ** -6, atol=5e-2)
+    assert torch.allclose(got, ref, **tol), float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", [(1, 9, 11, 3, 64), (2, 12, 20, 64, 16), (1, 7, 5, 40, 72)])
+def test_conv3x3_wgrad(dt, case):
+    n, h, w_, cin, cout = case
+    g = _gen(7)
+    x = torch.randn(n, cin, h, w_, generator=g)
+    dz = torch.randn(n, cout, h, w_, generator=g)
+    r = (lambda t: t) if dt == torch.float32 else _bf16r
+    wref = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(r(x).double(), wref, padding=1)
+    (gw,) = torch.autograd.grad(y, wref, r(dz).double())
+    gb = r(dz).double().sum(dim=(0, 2, 3))
+    dw = torch.full((cout, cin, 3, 3), 0.5, device=DEV)       # accumulates on top of existing .grad
+    db = torch.full((cout,), -1.0, device=DEV)
+    ops.conv3x3_wgrad(_nhwc(x, dt), _nhwc(dz, dt), dw, db)
+    assert torch.allclose(dw.cpu() - 0.5, gw.float(), rtol=1e-4, atol=2e-3), float((dw.cpu() - 0.5 - gw.float()).abs().max())
+    assert torch.allclose(db.cpu() + 1.0, gb.float(), rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1, 64, 480 // 8, 854 // 7), (2, 16, 7, 9), (1, 8, 1, 1), (1, 24, 30, 107)])
+def test_maxpool_fwd_bwd(dt, shape):
+    g = _gen(9)
+    x = torch.randn(shape, generator=g).clamp_min(0)          # ties at 0 like post-ReLU maps
+    r = (lambda t: t) if dt == torch.float32 else _bf16r
+    xr = r(x).requires_grad_(True)
+    ref = F.max_pool2d(xr, 2, 2, ceil_mode=True)
+    xd = _nhwc(x, dt)
+    y = ops.maxpool2x2(xd)
+    assert torch.equal(_nchw(y, shape[1]), ref.detach())
+    dy = r(torch.randn(ref.shape, generator=g))
+    (gref,) = torch.autograd.grad(ref, xr, dy)
+    dx = ops.maxpool2x2_bwd(xd, _nhwc(dy, dt))
+    assert torch.equal(_nchw(dx, shape[1]), gref)
+
+
+def _side_inputs(n, H, W, seed, dt):
+    g = _gen(seed)
+    hs, ws, h, w_ = [], [], H, W
+    sp_nchw = []
+    for i in range(4):
+        h, w_ = (h + 1) // 2, (w_ + 1) // 2
+        hs.append(h)
+        ws.append(w_)
+        sp_nchw.append(torch.randn(n, 16, h, w_, generator=g))
+    sd = {}
+    for i in range(4):
+        k = 4 << i
+        sd[f"upscale.{i}.weight"] = O.interp_surgery_weight(16, k)
+        sd[f"upscale_.{i}.weight"] = O.interp_surgery_weight(1, k)
+        sd[f"score_dsn.{i}.weight"] = torch.randn(1, 16, 1, 1, generator=g) * 0.3
+        sd[f"score_dsn.{i}.bias"] = torch.randn(1, generator=g)
+    sd["fuse.weight"] = torch.randn(1, 64, 1, 1, generator=g) * 0.2
+    sd["fuse.bias"] = torch.randn(1, generator=g)
+    return sp_nchw, sd
+
+
+def _side_ref(sp_nchw, sd, H, W):
+    side, side_out = [], []
+    for i in range(4):
+        s = 2 << i
+        side.append(O.center_crop(F.conv_transpose2d(sp_nchw[i], sd[f"upscale.{i}.weight"], stride=s), H, W))
+        sc = F.conv2d(sp_nchw[i], sd[f"score_dsn.{i}.weight"], sd[f"score_dsn.{i}.bias"])
+        side_out.append(O.center_crop(F.conv_transpose2d(sc, sd[f"upscale_.{i}.weight"], stride=s), H, W))
+    fused = F.conv2d(torch.cat(side, 1), sd["fuse.weight"], sd["fuse.bias"])
+    return side_out + [fused]
+
+
+def _side_params(sd):
+    d = {k: v.to(DEV) for k, v in sd.items()}
+    return ops.side_params_prepare([d[f"upscale.{i}.weight"] for i in range(4)], [d[f"upscale_.{i}.weight"] for i in range(4)],
+                                   [d[f"score_dsn.{i}.weight"] for i in range(4)], [d[f"score_dsn.{i}.bias"] for i in range(4)],
+                                   d["fuse.weight"], d["fuse.bias"]), d
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("general", [False, True])
+@pytest.mark.parametrize("HW", [(48, 72), (45, 70), (33, 17)])
+def test_side_chain_forward(dt, general, HW):
+    H, W = HW
+    sp, sd = _side_inputs(2, H, W, 11, dt)
+    r = (lambda t: t) if dt == torch.float32 else _bf16r
+    ref = _side_ref([r(t) for t in sp], sd, H, W)
+    params, dsd = _side_params(sd)
+    assert int(ops.side_check_diagonal([dsd[f"upscale.{i}.weight"] for i in range(4)]).item()) == 0
+    outs, prob, mask = ops.side_fwd([_nhwc(t, dt) for t in sp], params, H, W, general=general, want_prob=True, want_mask=True)
+    for a, b in zip(outs, ref):
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=2e-5), float((a.cpu() - b).abs().max())
+    p = O.probabilities(outs[4].cpu())
+    assert torch.allclose(prob.cpu(), p, atol=1e-6)
+    assert torch.equal(mask.cpu(), O.binarise(prob.cpu()))
+
+
+def test_side_chain_general_dense_upscale():
+    """Non-diagonal `upscale` weights (e.g. after an Adam step, prune.py:256): exact general path."""
+    H, W = 40, 56
+    sp, sd = _side_inputs(1, H, W, 13, torch.float32)
+    g = _gen(14)
+    for i in range(4):
+        sd[f"upscale.{i}.weight"] = sd[f"upscale.{i}.weight"] + 0.01 * torch.randn(sd[f"upscale.{i}.weight"].shape, generator=g)
+        sd[f"upscale_.{i}.weight"] = sd[f"upscale_.{i}.weight"] + 0.01 * torch.randn(sd[f"upscale_.{i}.weight"].shape, generator=g)
+    ref = _side_ref(sp, sd, H, W)
+    params, dsd = _side_params(sd)
+    assert int(ops.side_check_diagonal([dsd[f"upscale.{i}.weight"] for i in range(4)]).item()) > 0
+    outs, _, _ = ops.side_fwd([_nhwc(t, torch.float32) for t in sp], params, H, W, general=True)
+    for a, b in zip(outs, ref):
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=5e-5), float((a.cpu() - b).abs().max())
+
+
+@pytest.mark.parametrize("deep", [False, True])
+def test_side_chain_backward(deep):
+    H, W = 45, 70
+    n = 2
+    sp, sd = _side_inputs(n, H, W, 15, torch.float32)
+    g = _gen(16)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if not k.startswith("upscale")}
+    spl = [t.clone().requires_grad_(True) for t in sp]
+    full = dict(sd)
+    full.update(leaf)
+    outs = _side_ref(spl, full, H, W)
+    douts = [torch.randn(n, 1, H, W, generator=g) if (deep or i == 4) else None for i in range(5)]
+    loss = sum((o * d).sum() for o, d in zip(outs, douts) if d is not None)
+    loss.backward()
+    params, _ = _side_params(sd)
+    dfw = torch.zeros(1, 64, 1, 1, device=DEV)
+    dfb = torch.zeros(1, device=DEV)
+    dsw = [torch.zeros(1, 16, 1, 1, device=DEV) for _ in range(4)]
+    dsb = [torch.zeros(1, device=DEV) for _ in range(4)]
+    dsp = ops.side_bwd([_nhwc(t, torch.float32) for t in sp], params, [None if d is None else d.to(DEV) for d in douts],
+                       H, W, dfw, dfb, dsw, dsb)
+    for i in range(4):
+        assert torch.allclose(_nchw(dsp[i], 16), spl[i].grad, rtol=1e-4, atol=1e-4), i
+        if deep:
+            assert torch.allclose(dsw[i].cpu(), leaf[f"score_dsn.{i}.weight"].grad, rtol=1e-4, atol=1e-3)
+            assert torch.allclose(dsb[i].cpu(), leaf[f"score_dsn.{i}.bias"].grad, rtol=1e-4, atol=1e-3)
+        else:
+            assert float(dsw[i].abs().max()) == 0.0
+    assert torch.allclose(dfw.cpu(), leaf["fuse.weight"].grad, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(dfb.cpu(), leaf["fuse.bias"].grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 4, 4), (2, 1, 37, 53), (1, 1, 480, 854)])
+@pytest.mark.parametrize("size_average", [True, False])
+def test_balanced_loss(shape, size_average):
+    g = _gen(21)
+    out = torch.randn(shape, generator=g) * 4
+    lab = (torch.rand(shape, generator=g) > 0.7).float()
+    o = out.clone().requires_grad_(True)
+    ref = O.class_balanced_cross_entropy_loss(o, lab, size_average)
+    (gref,) = torch.autograd.grad(ref, o, torch.tensor(0.2))
+    loss, stats = ops.bal_loss_fwd(out.to(DEV), lab.to(DEV), size_average)
+    assert torch.allclose(loss.cpu(), ref.detach(), rtol=2e-5), (float(loss), float(ref))
+    assert int(stats[0].item()) == int(lab.sum().item()) and int(stats[1].item()) == int((1 - lab).sum().item())
+    dx = ops.bal_loss_bwd(out.to(DEV), lab.to(DEV), size_average, stats, torch.tensor(0.2, device=DEV))
+    assert torch.allclose(dx.cpu(), gref, rtol=1e-4, atol=1e-7 * float(gref.abs().max()) + 1e-12)
+
+
+def test_balanced_loss_golden_kat():
+    from fosvos_b200 import class_balanced_cross_entropy_loss
+    from conftest import GOLDEN
+    kat = torch.load(os.path.join(GOLDEN, "kat.pt"), weights_only=False)
+    for name in ["loss_4x4_sa1", "loss_4x4_sa0", "loss_2x1x37x53_sa1", "loss_2x1x37x53_sa0", "loss_teacher_logits"]:
+        c = kat[name]
+        out = c["output"].to(DEV).requires_grad_(True)
+        loss = class_balanced_cross_entropy_loss(out, c["label"].to(DEV), size_average=not name.endswith("sa0"))
+        assert loss.dim() == 0
+        assert torch.allclose(loss.detach().cpu(), c["loss"], rtol=2e-5), name
+        loss.backward()
+        assert torch.allclose(out.grad.cpu(), c["grad"], rtol=1e-4, atol=1e-7), name
+
+
+def test_fused_sgd_matches_reference_sgd():
+    from fosvos_b200 import FusedSGD
+    g = _gen(31)
+    shapes = [(64, 3, 3, 3), (64,), (5,), (16, 512, 3, 3), (1, 64, 1, 1), (1,), (4099,)]
+    ps = [torch.randn(s, generator=g) for s in shapes]
+    cfg = [(1e-2, 2e-4), (2e-2, 0.0), (0.0, 0.0), (1e-2, 2e-4), (1e-4, 2e-4), (2e-4, 0.0), (0.5, 0.1)]
+    mine = [torch.nn.Parameter(p.clone().to(DEV)) for p in ps]
+    opt = FusedSGD([dict(params=[m], lr=lr, weight_decay=wd) for m, (lr, wd) in zip(mine, cfg)], lr=1e-2, momentum=0.9)
+    ref = [p.clone() for p in ps]
+    bufs = [None] * len(ps)
+    for step in range(3):
+        grads = [torch.randn(s, generator=g) for s in shapes]
+        for m, gr in zip(mine, grads):
+            m.grad = gr.clone().to(DEV) if m.grad is None else m.grad.copy_(gr.to(DEV))
+        opt.step_and_zero()
+        for i, (lr, wd) in enumerate(cfg):
+            ref[i], bufs[i] = O.sgd_step(ref[i], grads[i], bufs[i], lr, wd, 0.9)
+        for m, r_ in zip(mine, ref):
+            assert torch.allclose(m.detach().cpu(), r_, rtol=1e-6, atol=1e-7)
+            assert float(m.grad.abs().max()) == 0.0
+    # and against torch.optim.SGD itself
+    tp = [torch.nn.Parameter(p.clone()) for p in ps]
+    topt = torch.optim.SGD([dict(params=[t], lr=lr, weight_decay=wd) for t, (lr, wd) in zip(tp, cfg)], lr=1e-2, momentum=0.9)
+    g2 = _gen(31)
+    _ = [torch.randn(s, generator=g2) for s in shapes]
+    for step in range(3):
+        for t, s in zip(tp, shapes):
+            t.grad = torch.randn(s, generator=g2)
+        topt.step()
+    for m, t in zip(mine, tp):
+        assert torch.allclose(m.detach().cpu(), t.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_mask_iou_bit_exact():
+    g = _gen(41)
+    a = (torch.rand(5, 1, 480, 854, generator=g) > 0.6).to(torch.uint8)
+    b = (torch.rand(5, 1, 480, 854, generator=g) > 0.5).to(torch.uint8)
+    a[3] = 0
+    b[3] = 0                                                   # empty masks: 0/0
+    counts = ops.mask_iou(a.to(DEV).view(5, -1), b.to(DEV).view(5, -1)).cpu()
+    for f in range(5):
+        assert tuple(counts[f].tolist()) == O.mask_iou_counts(a[f], b[f])
+    # odd length / unaligned tail
+    a1, b1 = a.view(5, -1)[:, :1001].contiguous(), b.view(5, -1)[:, :1001].contiguous()
+    c1 = ops.mask_iou(a1.to(DEV), b1.to(DEV)).cpu()
+    for f in range(5):
+        assert tuple(c1[f].tolist()) == O.mask_iou_counts(a1[f], b1[f])
+
+
+def test_sigmoid_threshold():
+    x = torch.randn(3, 1, 17, 19, generator=_gen(43)) * 5
+    x[0, 0, 0, 0] = 0.0
+    prob, mask = ops.sigmoid_threshold(x.to(DEV))
+    assert torch.allclose(prob.cpu(), O.probabilities(x), atol=1e-6)
+    assert torch.equal(mask.cpu(), O.binarise(prob.cpu()))
+    assert int(mask[0, 0, 0, 0]) == 1

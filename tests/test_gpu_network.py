@@ -1,0 +1,251 @@
+"""GPU: the drop-in OSVOS_VGG / loss / fine-tune step against the golden fixtures minted from the
+live reference (tests/golden, oracle/make_golden.py) and against the oracle at full size.
+
+Tolerances (BASELINE.json north_star): fp32 mode 1e-4 max-abs on sigmoid probabilities, bf16 mode
+1e-2; binarised masks >= 99.5 % IoU; J counts bit-exact on identical masks."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import fosvos_b200 as FB  # noqa: E402
+from fosvos_b200 import ops, synth  # noqa: E402
+from oracle import osvos_oracle as O  # noqa: E402
+from conftest import GOLDEN  # noqa: E402
+
+DEV = "cuda"
+TOL_PROB = {"fp32": 1e-4, "bf16": 1e-2, "bf16_simt": 1e-2}
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def _case(fix):
+    x, m = synth.make_frame(fix["seq"], fix["frame"], fix["H"], fix["W"], noise=fix.get("noise", False))
+    sd = synth.make_state_dict(0, fix["kind"])
+    sd = synth.calibrate(sd, O.vgg_forward, x, mask=m if fix["kind"] == "structured" else None)
+    return x, m, sd
+
+
+def _net(sd, precision):
+    net = FB.OSVOS_VGG(pretrained=0)
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    net.precision = precision
+    return net
+
+
+def _iou(a, b):
+    i, u = O.mask_iou_counts(a, b)
+    return 1.0 if u == 0 else i / u
+
+
+def test_state_dict_layout_matches_reference():
+    net = FB.OSVOS_VGG(pretrained=0)
+    kat = _load("kat.pt")
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == kat["state_dict_spec"]
+    assert sum(p.numel() for p in net.parameters()) == 15267157
+    for i, m in enumerate(net.upscale):
+        assert torch.equal(m.weight.data, O.interp_surgery_weight(16, 4 << i))
+    # optimizer group tables (network_provider.py:98-159)
+    id2k = {id(p): k for k, p in net.named_parameters()}
+    for mode, fn in (("online", FB.get_optimizer_online), ("offline", FB.get_optimizer_offline)):
+        opt = fn(net, fused=False)
+        table = kat[f"optimizer_groups_{mode}"]
+        assert [[id2k[id(p)] for p in g["params"]] for g in opt.param_groups] == [g["keys"] for g in table]
+        assert np.allclose([g["lr"] for g in opt.param_groups], [g["lr"] for g in table], rtol=1e-12, atol=0)
+        assert [g["weight_decay"] for g in opt.param_groups] == [g["weight_decay"] for g in table]
+        assert all(g["momentum"] == 0.9 for g in opt.param_groups)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16_simt", "bf16"])
+@pytest.mark.parametrize("name", ["fwd_48x72_random", "fwd_45x70_random", "fwd_64x96_structured"])
+def test_forward_golden(name, precision):
+    fix = _load(name + ".pt")
+    x, m, sd = _case(fix)
+    net = _net(sd, precision)
+    with torch.no_grad():
+        outs = net(x.to(DEV))
+    assert isinstance(outs, list) and len(outs) == 5
+    for o, ref in zip(outs, fix["outs"]):
+        assert o.shape == ref.shape and o.dtype == torch.float32
+        err = float((torch.sigmoid(o.cpu()) - torch.sigmoid(ref)).abs().max())
+        assert err <= TOL_PROB[precision], (name, precision, err)
+    if precision == "fp32":
+        assert float((outs[4].cpu() - fix["outs"][4]).abs().max()) < 5e-4
+    _, prob, mask = net.predict(x.to(DEV))
+    ref_mask = O.binarise(O.probabilities(fix["outs"][4]))
+    if fix["kind"] == "structured":
+        assert _iou(mask.cpu(), ref_mask) >= 0.995
+    assert torch.equal(mask.cpu(), O.binarise(prob.cpu()))
+
+
+def test_forward_pruned_golden():
+    fix = _load("fwd_48x72_pruned50.pt")
+    x, _ = synth.make_frame(fix["seq"], fix["frame"], fix["H"], fix["W"], noise=True)
+    sd = synth.calibrate(synth.prune_state_dict(synth.make_state_dict(0, "random"), fix["keep"]), O.vgg_forward, x)
+    net = FB.OSVOS_VGG(pretrained=0)
+    # prune-style surgery on the module (reference prune.py:490-514): narrower convs, bias=False
+    idxs = O.stage_conv_indices()
+    for si in range(5):
+        for mi in idxs[si]:
+            w = sd[f"stages.{si}.{mi}.weight"]
+            net.stages[si][mi] = torch.nn.Conv2d(w.shape[1], w.shape[0], 3, padding=1, bias=False)
+        if si > 0:
+            net.side_prep[si - 1] = torch.nn.Conv2d(sd[f"side_prep.{si - 1}.weight"].shape[1], 16, 3, padding=1)
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    for precision in ("fp32", "bf16"):
+        net.precision = precision
+        with torch.no_grad():
+            outs = net(x.to(DEV))
+        for o, ref in zip(outs, fix["outs"]):
+            assert float((torch.sigmoid(o.cpu()) - torch.sigmoid(ref)).abs().max()) <= TOL_PROB[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["fwd_48x72_random", "fwd_45x70_random"])
+def test_backward_golden(name, precision):
+    fix = _load(name + ".pt")
+    x, m, sd = _case(fix)
+    net = _net(sd, precision)
+    outs = net.forward(x.to(DEV))
+    loss = FB.class_balanced_cross_entropy_loss(outs[-1], m.to(DEV), size_average=False)
+    rt = 2e-5 if precision == "fp32" else 2e-2
+    assert abs(float(loss) - float(fix["loss"])) <= rt * abs(float(fix["loss"])) + (1e-3 if precision == "fp32" else 2.0)
+    loss.backward()
+    params = dict(net.named_parameters())
+    for k, gref in fix["grads"].items():
+        g = params[k].grad.cpu()
+        scale = float(gref.abs().max())
+        err = float((g - gref).abs().max())
+        if precision == "fp32":
+            assert err <= 2e-4 * scale + 1e-6, (k, err, scale)
+        else:
+            # bf16 activations/gradients: compare in the aggregate
+            rel = float((g - gref).norm() / (gref.norm() + 1e-12))
+            assert rel <= 0.05, (k, rel)
+    assert params["upscale.0.weight"].grad is None
+
+
+def test_finetune_golden_fp32():
+    fix = _load("fwd_48x72_random.pt")
+    x, m, sd = _case(fix)
+    ft = fix["finetune"]
+    net = _net(sd, "fp32")
+    opt = FB.get_optimizer_online(net, learning_rate=ft["learning_rate"])
+    losses = []
+    FB.finetune(net, x.to(DEV), m.to(DEV), ft["n_iters"], ft["avg_grad_every_n"], optimizer=opt, losses_out=losses)
+    assert np.allclose(losses, ft["losses"], rtol=2e-4), (losses, ft["losses"])
+    new_sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    for k, d in ft["deltas"].items():
+        mine = new_sd[k] - sd[k]
+        assert torch.allclose(mine, d, rtol=2e-3, atol=2e-7 * max(1.0, float(sd[k].abs().max())) + 1e-3 * float(d.abs().max())), k
+    for k in sd:
+        if k.startswith("score_dsn") or k.startswith("upscale"):
+            assert torch.equal(new_sd[k], sd[k]), k            # never updated online (network_provider.py:144-159)
+    with torch.no_grad():
+        fused = net(x.to(DEV))[-1].cpu()
+    assert float((torch.sigmoid(fused) - torch.sigmoid(ft["fused_after"])).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("precision,use_graph", [("fp32", True), ("bf16", False), ("bf16", True)])
+def test_finetune_variants_track_golden(precision, use_graph):
+    """CUDA-graph replay and the bf16 tcgen05 path follow the same loss trajectory."""
+    fix = _load("fwd_48x72_random.pt")
+    x, m, sd = _case(fix)
+    ft = fix["finetune"]
+    net = _net(sd, precision)
+    opt = FB.get_optimizer_online(net, learning_rate=ft["learning_rate"])
+    losses = []
+    FB.finetune(net, x.to(DEV), m.to(DEV), ft["n_iters"], ft["avg_grad_every_n"], optimizer=opt, use_graph=use_graph,
+                losses_out=losses)
+    rt = 2e-4 if precision == "fp32" else 5e-2
+    assert np.allclose(losses, ft["losses"], rtol=rt), (losses, ft["losses"])
+    with torch.no_grad():
+        fused = net(x.to(DEV))[-1].cpu()
+    assert float((torch.sigmoid(fused) - torch.sigmoid(ft["fused_after"])).abs().max()) <= TOL_PROB[precision]
+
+
+def test_autograd_path_with_torch_sgd_matches_fused_trainer():
+    """Reference-style loop (autograd + optimizer.step/zero_grad, train_online.py:75-101) on the
+    drop-in module == the fused trainer."""
+    fix = _load("fwd_48x72_random.pt")
+    x, m, sd = _case(fix)
+    ft = fix["finetune"]
+    net = _net(sd, "fp32")
+    opt = FB.get_optimizer_online(net, learning_rate=ft["learning_rate"], fused=False)
+    xd, md = x.to(DEV), m.to(DEV)
+    losses, counter = [], 0
+    for it in range(ft["n_iters"]):
+        outputs = net.forward(xd)
+        loss = FB.class_balanced_cross_entropy_loss(outputs[-1], md, size_average=False)
+        losses.append(loss.item())
+        loss /= ft["avg_grad_every_n"]
+        loss.backward()
+        counter += 1
+        if counter % ft["avg_grad_every_n"] == 0:
+            opt.step()
+            opt.zero_grad()
+            counter = 0
+    assert np.allclose(losses, ft["losses"], rtol=2e-4)
+
+
+def test_offline_deep_supervision_backward():
+    """All five losses with the (1 - epoch/n_epochs) weight (train_offline.py:84-88)."""
+    fix = _load("fwd_45x70_random.pt")
+    x, m, sd = _case(fix)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    outs = O.vgg_forward(params, x)
+    ls = [O.class_balanced_cross_entropy_loss(o, m, size_average=False) for o in outs]
+    ref = 0.75 * sum(ls[:-1]) + ls[-1]
+    ref.backward()
+    net = _net(sd, "fp32")
+    outs = net.forward(x.to(DEV))
+    ls = [FB.class_balanced_cross_entropy_loss(o, m.to(DEV), size_average=False) for o in outs]
+    loss = 0.75 * sum(ls[:-1]) + ls[-1]
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    loss.backward()
+    mine = dict(net.named_parameters())
+    for k in ["score_dsn.0.weight", "score_dsn.3.bias", "fuse.weight", "side_prep.2.weight", "stages.3.1.bias", "stages.0.0.weight"]:
+        g, gr = mine[k].grad.cpu(), params[k].grad
+        assert float((g - gr).abs().max()) <= 3e-4 * float(gr.abs().max()) + 1e-6, k
+
+
+def test_hooks_and_module_surface():
+    """What prune/mimic-style consumers touch (prune.py:49-50,96-103; mimic.py:204-217)."""
+    net = FB.OSVOS_VGG(pretrained=0)
+    convs = [m for m in net.modules() if isinstance(m, torch.nn.Conv2d)]
+    assert len(convs) == 13 + 4 + 4 + 1
+    assert all(hasattr(c, a) for c in convs for a in ("in_channels", "out_channels", "kernel_size", "stride", "padding", "weight"))
+    assert len([m for m in net.modules() if isinstance(m, torch.nn.ConvTranspose2d)]) == 8
+    assert [n for n, _ in net.named_children()] == ["upscale", "upscale_", "stages", "side_prep", "score_dsn", "fuse"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_480x854_against_oracle(precision):
+    """BASELINE configs[0]/[1] frame size: one 480x854 frame, oracle on the host cores."""
+    x, m = synth.make_frame(0, 0, 480, 854)
+    xs, ms = synth.make_frame(0, 0, 120, 214)
+    sd = synth.calibrate(synth.make_state_dict(0, "structured"), O.vgg_forward, xs, mask=ms)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        ref = O.vgg_forward(sd, x)
+    net = _net(sd, precision)
+    outs, prob, mask = net.predict(x.to(DEV))
+    for o, r in zip(outs, ref):
+        err = float((torch.sigmoid(o.cpu()) - torch.sigmoid(r)).abs().max())
+        assert err <= TOL_PROB[precision], (precision, err)
+    ref_mask = O.binarise(O.probabilities(ref[4]))
+    iou = _iou(mask.cpu(), ref_mask)
+    assert iou >= 0.995, iou
+    # J counts from identical masks are bit-exact
+    counts = FB.region_iou(mask, ref_mask.to(DEV)).cpu()
+    assert tuple(counts[0].tolist()) == O.mask_iou_counts(mask.cpu(), ref_mask)
+    # batch > 1 gives the same per-frame result
+    outs2, _, mask2 = net.predict(torch.cat([x, x.flip(3)]).to(DEV))
+    assert torch.equal(mask2[0].cpu(), mask[0].cpu())

@@ -1,0 +1,141 @@
+"""CPU: host logic, the C-ABI surface, loud failure without a GPU, sharding (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import fosvos_b200 as FB
+from fosvos_b200 import _lib as L, synth
+from oracle import osvos_oracle as O
+from conftest import ROOT
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "fosvos_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fosvos_[a-z0-9_]+)\s*\(", src)) - {"fosvos_sgd_entry"})
+
+
+def test_library_exports_every_declared_symbol():
+    from fosvos_b200.build import build
+    build()
+    lib = ctypes.CDLL(L.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/fosvos_b200.h but not exported"
+    assert sorted(L.SIGNATURES) == names, "ctypes binding and header disagree"
+    assert L.lib().fosvos_abi_version() >= 1
+    assert L.lib().fosvos_side_params_bytes() == 4 * (4 + 4 * 36 + 18 * (16 + 64 + 256 + 1024))
+
+
+def test_no_cpu_fallback():
+    net = FB.OSVOS_VGG(pretrained=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 3, 16, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FB.class_balanced_cross_entropy_loss(torch.zeros(1, 1, 4, 4), torch.ones(1, 1, 4, 4))
+    if not torch.cuda.is_available():
+        assert L.lib().fosvos_device_check(0) == -3
+        assert "no CPU fallback" in L.last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "fosvos_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+def test_module_surface_and_state_dict():
+    net = FB.OSVOS_VGG(pretrained=0)
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == O.state_dict_spec()
+    sd = synth.make_state_dict(0)
+    net.load_state_dict(sd)                              # strict
+    assert all(torch.equal(net.state_dict()[k], sd[k]) for k in sd)
+    # default init statistics (osvos_vgg.py:97-111)
+    fresh = FB.OSVOS_VGG(pretrained=0)
+    w = fresh.stages[2][3].weight
+    assert abs(float(w.std()) - 1e-3) < 1e-4 and float(fresh.stages[2][3].bias.abs().max()) == 0.0
+    assert torch.equal(fresh.upscale_[1].weight.data[0, 0], torch.from_numpy(FB.upsample_filt(8)).float())
+    with pytest.raises(Exception, match="channels need to be the same"):
+        FB.interp_surgery(torch.nn.ConvTranspose2d(2, 3, 4))
+    # whole-module pickling as NetworkProvider.save_model does (network_provider.py:60-63)
+    import io
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    net2 = torch.load(buf, weights_only=False)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+
+
+def test_layer_helpers_match_oracle():
+    import numpy as np
+    for k in (3, 4, 5, 8, 16, 32):
+        assert np.array_equal(FB.upsample_filt(k), O.upsample_filt(k))
+    x = torch.arange(13 * 9, dtype=torch.float32).view(1, 1, 13, 9)
+    assert torch.equal(FB.center_crop(x, 8, 4), O.center_crop(x, 8, 4))
+    x = torch.arange(483 * 857, dtype=torch.float32).view(1, 1, 483, 857)
+    assert FB.center_crop(x, 480, 854)[0, 0, 0, 0] == 857 + 1
+
+
+def test_optimizer_groups_and_fused_sgd_config():
+    net = FB.OSVOS_VGG(pretrained=0)
+    id2k = {id(p): k for k, p in net.named_parameters()}
+    for mode, fn in (("online", FB.get_optimizer_online), ("offline", FB.get_optimizer_offline)):
+        for fused in (True, False):
+            opt = fn(net, fused=fused)
+            mine = [dict(keys=[id2k[id(p)] for p in g["params"]], lr=g["lr"], weight_decay=g["weight_decay"]) for g in opt.param_groups]
+            ref = O.optimizer_groups(list(id2k.values()), mode)
+            assert [m["keys"] for m in mine] == [r["keys"] for r in ref]
+            assert all(abs(m["lr"] - r["lr"]) < 1e-22 and m["weight_decay"] == r["weight_decay"] for m, r in zip(mine, ref))
+    with pytest.raises(ValueError):
+        FB.FusedSGD(net.parameters(), lr=0.1, nesterov=True, momentum=0.9)
+
+
+def test_sequence_sharding_rule():
+    seqs = list(range(20))
+    parts = [FB.sequences_for_rank(seqs, r, 8) for r in range(8)]
+    assert sorted(sum(parts, [])) == seqs
+    assert [len(p) for p in parts] == [3, 3, 3, 3, 2, 2, 2, 2]
+    assert parts[1] == [1, 9, 17]                        # i % group_size == group (train_online.py:184-186)
+
+
+def test_synth_is_deterministic():
+    a, ma = synth.make_frame(2, 5, 48, 72)
+    b, mb = synth.make_frame(2, 5, 48, 72)
+    assert torch.equal(a, b) and torch.equal(ma, mb)
+    assert 0.05 < float(ma.mean()) < 0.35
+    c, _ = synth.make_frame(2, 6, 48, 72)
+    assert not torch.equal(a, c)
+    sd1, sd2 = synth.make_state_dict(0), synth.make_state_dict(0)
+    assert all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    p = synth.prune_state_dict(sd1, 0.5)
+    assert p["stages.4.5.weight"].shape == (256, 256, 3, 3) and "stages.0.0.bias" not in p
+
+
+def test_bench_sharding_two_ranks_gloo(tmp_path):
+    """world_size-2 run of the multi-GPU plumbing (sequence sharding + max-over-ranks reduce) on CPU/gloo."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from fosvos_b200.sharding import init_distributed, max_over_ranks, sum_over_ranks\n"
+        "from fosvos_b200 import sequences_for_rank\n"
+        "rank, world = init_distributed(backend='gloo')\n"
+        "mine = sequences_for_rank(list(range(5)), rank, world)\n"
+        "t = max_over_ranks(float(10 + rank), device='cpu')\n"
+        "n = sum_over_ranks(float(len(mine)), device='cpu')\n"
+        "assert t == 11.0 and n == 5.0, (t, n)\n"
+        "print('rank', rank, mine, flush=True)\n"
+        "dist.destroy_process_group()\n")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 [0, 2, 4]" in r.stdout and "rank 1 [1, 3]" in r.stdout
