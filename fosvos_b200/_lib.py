@@ -74,7 +74,12 @@ def last_error() -> str:
     return lib().fosvos_last_error().decode("utf-8", "replace")
 
 
+# number of ABI compute calls issued (each enqueues >= 1 kernel); graph replays add their node count
+CALLS = [0]
+
+
 def check(rc: int, what: str = "") -> None:
+    CALLS[0] += 1
     if rc != 0:
         raise RuntimeError(f"fosvos_b200 {what} failed (status {rc}): {last_error()}")
 

@@ -77,7 +77,9 @@ def finetune(net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, n_iters: i
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
+            calls0 = L.CALLS[0]
             micro.run()
+            calls_per_replay = L.CALLS[0] - calls0
             for g in micro.grads.values():
                 g.zero_()
             micro.loss_sum.zero_()
@@ -92,6 +94,7 @@ def finetune(net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, n_iters: i
     for _ in range(n_iters):
         if graph is not None:
             graph.replay()
+            L.CALLS[0] += calls_per_replay
         else:
             micro.run()
         if losses_out is not None:

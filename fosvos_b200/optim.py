@@ -42,7 +42,7 @@ class FusedSGD(Optimizer):
                 st = self.state[p]
                 if "momentum_buffer" not in st or st["momentum_buffer"] is None:
                     st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                ent.append((p.data, p.grad, st["momentum_buffer"], float(g["lr"]), float(g["weight_decay"])))
+                ent.append((p, p.grad, st["momentum_buffer"], float(g["lr"]), float(g["weight_decay"])))
         return ent
 
     def _ensure_table(self):
@@ -54,7 +54,7 @@ class FusedSGD(Optimizer):
             else:
                 dev = ent[0][0].device
                 L.require_device(dev)
-                self._table = ops.sgd_table(ent, dev) + (len(ent),)
+                self._table = ops.sgd_table([(p.detach(), g, b, lr, wd) for p, g, b, lr, wd in ent], dev) + (len(ent),)
             self._table_key = key
         return ent
 
@@ -71,7 +71,7 @@ class FusedSGD(Optimizer):
         ops.sgd_step(table, prefix, n_tensors, n_chunks, self._momentum, zero_grad)
         for p, _, _, lr, _ in ent:
             if lr != 0.0:
-                torch.autograd.graph.increment_version(p)   # derived (packed) weight copies must be rebuilt
+                torch.autograd.graph.increment_version(p)   # the Parameter's own counter: packed copies get rebuilt
         return loss
 
     def step_and_zero(self):
