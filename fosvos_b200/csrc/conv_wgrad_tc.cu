@@ -1,0 +1,347 @@
+// Weight gradient of the 3x3 convolution on the 5th-generation tensor cores.
+//
+//   dW[co][ci][tap] = sum_{pixels p} dZ[p][co] * X[p + tap][ci]            bf16 x bf16 -> fp32
+//
+// GEMM-K is the PIXEL dimension, so both operands are "MN-major": NHWC rows (one pixel = one
+// 128-byte row of 64 channels) are exactly the SWIZZLE_128B MN-major canonical layout, and a
+// 16-pixel K step is 16 consecutive rows.  One work item = (128-row M tile, N tile, kernel column
+// s, pixel range); its three accumulators (kernel rows r = 0..2) live in TMEM side by side.
+// Per 128-pixel patch (TH x TW, TW % 8 == 0) the CTA loads
+//   - the un-shifted operand:  boxes {64ch, TW, TH, 1}
+//   - the shifted operand X:   boxes {64ch, TW, TH+2, 1} at (x0+s-1, y0-1)  -- ONE halo box serves the
+//     three vertical taps: tap r starts r*TW rows (a multiple of the 1024-byte swizzle atom) further.
+// TMA zero-fills out-of-frame rows (= the convolution padding) and channel tails.
+// Orientation is chosen per layer so that M = 128 is well filled:
+//   X_IS_A = 0:  M = cout (dZ is A), N = cin tile      -> workspace [tap][cout][cin]
+//   X_IS_A = 1:  M = cin  (X  is A), N = cout tile     -> workspace [tap][cin][cout]   (side_prep, N = 16)
+// Split-K partial sums are merged with vectorised fp32 reductions (red.global.add.v4.f32) into a
+// [tap][M][N] workspace; `wgrad_unpack_kernel` then adds it into the OIHW fp32 .grad tensor.
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fosvos {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_PLAIN_BLOCK = 128 * 128;          // bytes of one un-shifted 64-channel box (128 px)
+
+struct WgParams {
+  float* ws;                 // [9][Mtot][Ntot] fp32
+  int N, H, W;
+  int Mtot, Ntot;            // padded channel counts of the M and N dimensions
+  int m_tiles, n_tiles, splits;
+  int n_cols;                // N extent per tap (16, 64 or 128)
+  int nb_n;                  // 64-channel boxes per N tile
+  int tiles_x, tiles_y, patches;
+  int tw_shift;              // TW = 1 << tw_shift (>= 8)
+  int x_is_a;
+  int stages, stage_bytes, a_bytes;
+  int x_block;               // bytes of one shifted 64-channel box: (TH+2)*TW*128
+};
+
+// MN-major SWIZZLE_128B operand: rows (K) of 128 B, 8-row groups SBO = 1024 B apart, 64-element
+// MN blocks LBO bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* done_bar = empty_bar + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_z);
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_ptr, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // work item
+  int item = blockIdx.x;
+  const int split = item % p.splits; item /= p.splits;
+  const int s = item % 3; item /= 3;
+  const int nt = item % p.n_tiles;
+  const int mt = item / p.n_tiles;
+  const int p_begin = (int)((long long)p.patches * split / p.splits);
+  const int p_end = (int)((long long)p.patches * (split + 1) / p.splits);
+  const int TW = 1 << p.tw_shift, TH = 128 >> p.tw_shift;
+  const int m0 = mt * 128, n0 = nt * p.n_cols;
+  // channel origins of the two operands
+  const int xc0 = p.x_is_a ? m0 : n0;          // X channels (cin)
+  const int zc0 = p.x_is_a ? n0 : m0;          // dZ channels (cout)
+  const int nb_x = p.x_is_a ? 2 : p.nb_n;
+  const int nb_z = p.x_is_a ? p.nb_n : 2;
+  const int x_off = p.x_is_a ? 0 : p.a_bytes;  // byte offset of the X boxes inside a stage
+  const int z_off = p.x_is_a ? p.a_bytes : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = p_begin; pt < p_end; ++pt) {
+        int t = pt;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int n = t / p.tiles_y;
+        const int x0 = tx * TW, y0 = ty * TH;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * p.stage_bytes;
+        ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+        for (int j = 0; j < nb_x; ++j)
+          ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], xc0 + 64 * j, x0 + s - 1, y0 - 1, n);
+        for (int j = 0; j < nb_z; ++j)
+          ptx::tma_load_4d(st + z_off + j * WG_PLAIN_BLOCK, &map_z, &full_bar[stage], zc0 + 64 * j, x0, y0, n);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // kind::f16, D fp32, A/B bf16, both MN-major (bits 15/16), M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lbo_a = p.x_is_a ? p.x_block : WG_PLAIN_BLOCK;
+      const uint32_t lbo_b = p.x_is_a ? WG_PLAIN_BLOCK : p.x_block;
+      const uint32_t tap_bytes = (uint32_t)TW * 128;       // one image row of the patch
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = p_begin; pt < p_end; ++pt) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t st = ptx::smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t a_base = st, b_base = st + p.a_bytes;
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t a_r = a_base + (p.x_is_a ? r * tap_bytes : 0);
+          const uint32_t b_r = b_base + (p.x_is_a ? 0 : r * tap_bytes);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t da = umma_desc_sw128_mnmajor(a_r + kk * 2048, lbo_a);
+            const uint64_t db = umma_desc_sw128_mnmajor(b_r + kk * 2048, lbo_b);
+            ptx::umma_bf16(tmem_base + r * p.n_cols, da, db, idesc, (pt != p_begin) || (kk != 0));
+          }
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(done_bar);
+    }
+  } else {
+    // ===================== epilogue: TMEM -> vectorised fp32 reductions =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    if (p_end > p_begin) {
+      ptx::mbar_wait(done_bar, 0);
+      ptx::tc_fence_after();
+      const bool row_ok = (m0 + row) < p.Mtot;
+#pragma unroll 1
+      for (int r = 0; r < 3; ++r) {
+        const int tap = r * 3 + s;
+        float* dst = p.ws + ((long long)tap * p.Mtot + (m0 + row)) * p.Ntot + n0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * p.n_cols;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.n_cols; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld16(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (n0 + c0 + 4 * q < p.Ntot)
+                red_add_v4(dst + c0 + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dw_oihw[co][ci][tap] += ws[tap][a][b];  ws is [tap][cout][cin] (x_is_a = 0) or [tap][cin][cout]
+__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int CoutP,
+                                    int CinP, int x_is_a) {
+  const int total = Cout * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // fastest index follows the workspace's contiguous dimension -> coalesced reads
+    int co, ci;
+    if (x_is_a) { co = i % Cout; ci = i / Cout; } else { ci = i % Cin; co = i / Cin; }
+    const long long plane = (long long)CoutP * CinP;
+    const long long src = x_is_a ? ((long long)ci * CoutP + co) : ((long long)co * CinP + ci);
+    float* d = dw + ((long long)co * Cin + ci) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) d[t] += ws[t * plane + src];
+  }
+}
+
+// db[co] += sum over pixels of dz[p][co]
+template <typename T>
+__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dz, float* __restrict__ db, long long pixels, int CoutP, int Cout) {
+  const int groups = CoutP / 8;
+  const int g = threadIdx.x % groups;               // blockDim.x is a multiple of groups (host guarantees)
+  const int lanes = blockDim.x / groups;
+  const int pl = threadIdx.x / groups;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long px = (long long)blockIdx.x * lanes + pl; px < pixels; px += (long long)gridDim.x * lanes) {
+    float v[8];
+    load8(dz + px * CoutP + g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  __shared__ float sm[512];
+  for (int i = threadIdx.x; i < CoutP; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&sm[g * 8 + j], acc[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) atomicAdd(db + i, sm[i]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn wg_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+static int wg_encode(CUtensorMap* m, const void* x, int N, int H, int W, int C, int TW, int rows) {
+  EncodeTiledFn enc = wg_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wgrad %dx%dx%dx%d box %dx%d) failed: %d", N, H, W, C, rows, TW, (int)r); return FOSVOS_ERR_DRIVER; }
+  return FOSVOS_OK;
+}
+
+}  // namespace fosvos
+
+using namespace fosvos;
+
+extern "C" {
+
+size_t fosvos_conv3x3_wgrad_tc_workspace_bytes(int CinP, int CoutP) { return (size_t)9 * CinP * CoutP * sizeof(float); }
+
+int fosvos_conv3x3_wgrad_tc(const void* x, const void* dz, float* dw, float* db, void* workspace, int N, int H, int W,
+                            int CinP, int CoutP, int Cin, int Cout, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(x && dz && dw && workspace && N > 0 && H > 0 && W > 0, "conv3x3_wgrad_tc: null pointer or empty shape");
+  FOSVOS_REQUIRE(CinP % 8 == 0 && CoutP % 8 == 0 && CinP > 0 && CoutP > 0 && Cin > 0 && Cin <= CinP && Cout > 0 && Cout <= CoutP,
+                 "conv3x3_wgrad_tc: bad channel counts (CinP=%d CoutP=%d Cin=%d Cout=%d)", CinP, CoutP, Cin, Cout);
+  FOSVOS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dz & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+                 "conv3x3_wgrad_tc: pointers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  WgParams p;
+  p.ws = (float*)workspace;
+  p.N = N; p.H = H; p.W = W;
+  // orientation: put the wider channel dimension on M (=128 rows); tiny couts (side_prep) go to N
+  p.x_is_a = (CoutP < 64 || (CinP >= 128 && CoutP < 128)) ? 1 : 0;
+  p.Mtot = p.x_is_a ? CinP : CoutP;
+  p.Ntot = p.x_is_a ? CoutP : CinP;
+  p.n_cols = p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
+  p.nb_n = (p.n_cols + 63) / 64;
+  p.m_tiles = ceil_div(p.Mtot, 128);
+  p.n_tiles = ceil_div(p.Ntot, p.n_cols);
+  // 128-pixel patch with TW % 8 == 0 that wastes the fewest out-of-frame pixels
+  int best = 3; long long best_area = -1;
+  for (int sh = 3; sh <= 6; ++sh) {
+    const int TW = 1 << sh, TH = 128 >> sh;
+    const long long area = (long long)ceil_div(H, TH) * TH * ceil_div(W, TW) * TW;
+    if (best_area < 0 || area < best_area) { best_area = area; best = sh; }
+  }
+  p.tw_shift = best;
+  const int TW = 1 << best, TH = 128 >> best;
+  p.tiles_x = ceil_div(W, TW);
+  p.tiles_y = ceil_div(H, TH);
+  p.patches = N * p.tiles_x * p.tiles_y;
+  p.x_block = (TH + 2) * TW * 128;
+  const int nb_x = p.x_is_a ? 2 : p.nb_n, nb_z = p.x_is_a ? p.nb_n : 2;
+  const int x_bytes = nb_x * p.x_block, z_bytes = nb_z * WG_PLAIN_BLOCK;
+  p.a_bytes = p.x_is_a ? x_bytes : z_bytes;
+  p.stage_bytes = x_bytes + z_bytes;
+  p.stages = min(6, (220 * 1024 - 2048) / p.stage_bytes);
+  FOSVOS_REQUIRE(p.stages >= 2, "conv3x3_wgrad_tc: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+  const int items = p.m_tiles * p.n_tiles * 3;
+  int splits = max(1, (2 * num_sms()) / items);
+  splits = min(splits, p.patches);
+  p.splits = splits;
+
+  CUtensorMap mx, mz;
+  int rc = wg_encode(&mx, x, N, H, W, CinP, TW, TH + 2);
+  if (rc) return rc;
+  rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, TH);
+  if (rc) return rc;
+
+  cudaMemsetAsync(workspace, 0, fosvos_conv3x3_wgrad_tc_workspace_bytes(CinP, CoutP), st);
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 1024;
+  static int smem_set = 0;
+  if (smem_bytes > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad smem): %s", cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
+    smem_set = 227 * 1024;
+  }
+  conv3x3_wgrad_tc_kernel<<<items * splits, WG_THREADS, smem_bytes, st>>>(mx, mz, p);
+  rc = check_launch("conv3x3_wgrad_tc");
+  if (rc) return rc;
+  wgrad_unpack_kernel<<<min(num_sms() * 8, ceil_div(Cout * Cin, 256)), 256, 0, st>>>(p.ws, dw, Cout, Cin, CoutP, CinP, p.x_is_a);
+  rc = check_launch("wgrad_unpack");
+  if (rc) return rc;
+  if (db) {
+    FOSVOS_REQUIRE(CoutP <= 512, "conv3x3_wgrad_tc: bias gradient supports up to 512 output channels");
+    const int groups = CoutP / 8;
+    const int threads = max(groups, (256 / groups) * groups);
+    const long long pixels = (long long)N * H * W;
+    const int blocks = (int)min((long long)num_sms() * 4, ceil_div_ll(pixels, threads / groups));
+    bias_grad_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)dz, db, pixels, CoutP, Cout);
+    rc = check_launch("bias_grad");
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -142,6 +142,11 @@ class OSVOS_VGG(nn.Module):
             return "simt"
         raise RuntimeError(f"fosvos_b200: unknown precision mode '{self.precision}'")
 
+    def _wgrad_impl(self, cin_p: int) -> str:
+        # the tensor-core weight gradient needs a reasonably filled 64-channel K-slab of X; the 3-channel
+        # first layer (padded to 8) stays on the direct kernel
+        return "tc" if (self._impl() == "tc" and cin_p >= 32) else "simt"
+
     def _packed_for(self, conv: nn.Conv2d, need_dgrad: bool) -> _PackedConv:
         pc = self._packed.setdefault(id(conv), _PackedConv())
         b = conv.bias
@@ -242,7 +247,8 @@ class OSVOS_VGG(nn.Module):
             if si > 0:
                 spc = self.side_prep[si - 1]
                 pc = self._packed_for(spc, need_dgrad=True)
-                ops.conv3x3_wgrad(a_out, dsp[si - 1], grads[f"side_prep.{si - 1}.weight"], g(f"side_prep.{si - 1}.bias"))
+                ops.conv3x3_wgrad(a_out, dsp[si - 1], grads[f"side_prep.{si - 1}.weight"], g(f"side_prep.{si - 1}.bias"),
+                                  impl=self._wgrad_impl(a_out.shape[3]))
                 flags = L.CONV_MASK | (L.CONV_ACCUMULATE if dA is not None else 0)
                 dA = ops.conv3x3(dsp[si - 1], pc.w_dgrad, None, a_out.shape[3], flags, mask=a_out, out=dA, impl=impl)
             dz = dA
@@ -251,7 +257,7 @@ class OSVOS_VGG(nn.Module):
                 k = first[si] + j
                 x_in = saved["conv_in"][k]
                 name = names[si][j]
-                ops.conv3x3_wgrad(x_in, dz, grads[name + ".weight"], g(name + ".bias"))
+                ops.conv3x3_wgrad(x_in, dz, grads[name + ".weight"], g(name + ".bias"), impl=self._wgrad_impl(x_in.shape[3]))
                 if si == 0 and j == 0:
                     break
                 pc = self._packed_for(conv, need_dgrad=True)

@@ -85,14 +85,21 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
-def conv3x3_wgrad(x: torch.Tensor, dz: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
-    """dw (OIHW fp32) += x (*) dz ; db += sum dz.  Accumulates in place."""
+def conv3x3_wgrad(x: torch.Tensor, dz: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor], impl: str = "simt") -> None:
+    """dw (OIHW fp32) += x (*) dz ; db += sum dz.  Accumulates in place.
+    impl 'tc': tcgen05 kernel (bf16 operands); 'simt': direct fp32-FMA kernel."""
     L.require_device(x.device)
     n, h, w, cin_p = x.shape
     cout_p = dz.shape[3]
     cout, cin = dw.shape[0], dw.shape[1]
     assert dz.shape[:3] == x.shape[:3] and dw.dtype == torch.float32 and dw.is_contiguous()
     assert x.dtype == dz.dtype and x.is_contiguous() and dz.is_contiguous()
+    if impl == "tc":
+        assert x.dtype == torch.bfloat16
+        ws = torch.empty(L.lib().fosvos_conv3x3_wgrad_tc_workspace_bytes(cin_p, cout_p), dtype=torch.uint8, device=x.device)
+        L.check(L.lib().fosvos_conv3x3_wgrad_tc(x.data_ptr(), dz.data_ptr(), dw.data_ptr(), L.ptr(db), ws.data_ptr(), n, h, w,
+                                                cin_p, cout_p, cin, cout, L.stream()), "conv3x3_wgrad_tc")
+        return
     L.check(L.lib().fosvos_conv3x3_wgrad_simt(x.data_ptr(), dz.data_ptr(), dw.data_ptr(), L.ptr(db), n, h, w, cin_p, cout_p,
                                               cin, cout, L.dtype_code(x.dtype), L.stream()), "conv3x3_wgrad_simt")
 

@@ -119,6 +119,14 @@ int fosvos_conv3x3_wgrad_simt(const void* x, const void* dz, float* dw_oihw, flo
                               int W, int CinP, int CoutP, int Cin, int Cout, int dtype,
                               fosvos_stream_t stream);
 
+/* Same gradient on the tensor cores (bf16 operands, fp32 accumulation in TMEM; GEMM-K = pixels,
+ * split-K merged by vectorised fp32 reductions).  `workspace`: fosvos_conv3x3_wgrad_tc_workspace_bytes
+ * bytes of scratch ([tap][M][N] fp32), overwritten by the call. */
+size_t fosvos_conv3x3_wgrad_tc_workspace_bytes(int CinP, int CoutP);
+int fosvos_conv3x3_wgrad_tc(const void* x, const void* dz, float* dw_oihw, float* db, void* workspace,
+                            int N, int H, int W, int CinP, int CoutP, int Cin, int Cout,
+                            fosvos_stream_t stream);
+
 /* ---- 2x2 / stride-2 max pooling, ceil_mode=True (nn.MaxPool2d, osvos_vgg.py:90) ---- */
 int fosvos_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype,
                           fosvos_stream_t stream);

@@ -143,6 +143,25 @@ def test_conv3x3_wgrad(dt, case):
     assert torch.allclose(db.cpu() + 1.0, gb.float(), rtol=1e-4, atol=2e-3)
 
 
+@pytest.mark.parametrize("case", [(1, 16, 24, 64, 64), (1, 17, 23, 64, 128), (2, 9, 30, 128, 16), (1, 33, 40, 256, 256),
+                                  (1, 30, 54, 512, 512), (1, 12, 20, 40, 72), (1, 8, 8, 128, 128)])
+def test_conv3x3_wgrad_tc(case):
+    """tcgen05 weight gradient (MN-major operands, halo-box tap reuse, split-K reductions)."""
+    n, h, w_, cin, cout = case
+    g = _gen(17)
+    x = _bf16r(torch.randn(n, cin, h, w_, generator=g))
+    dz = _bf16r(torch.randn(n, cout, h, w_, generator=g))
+    wref = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    (gw,) = torch.autograd.grad(F.conv2d(x.double(), wref, padding=1), wref, dz.double())
+    gb = dz.double().sum(dim=(0, 2, 3))
+    dw = torch.full((cout, cin, 3, 3), 0.25, device=DEV)
+    db = torch.full((cout,), -2.0, device=DEV)
+    ops.conv3x3_wgrad(_nhwc(x, torch.bfloat16), _nhwc(dz, torch.bfloat16), dw, db, impl="tc")
+    err = float((dw.cpu() - 0.25 - gw.float()).abs().max())
+    assert torch.allclose(dw.cpu() - 0.25, gw.float(), rtol=1e-4, atol=5e-3), err
+    assert torch.allclose(db.cpu() + 2.0, gb.float(), rtol=1e-4, atol=5e-3)
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(1, 64, 480 // 8, 854 // 7), (2, 16, 7, 9), (1, 8, 1, 1), (1, 24, 30, 107)])
 def test_maxpool_fwd_bwd(dt, shape):
