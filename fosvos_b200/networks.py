@@ -152,16 +152,18 @@ class OSVOS_VGG(nn.Module):
         b = conv.bias
         key = (conv.weight.data_ptr(), conv.weight._version, None if b is None else (b.data_ptr(), b._version),
                self.precision, tuple(conv.weight.shape))
-        if pc.key != key:
-            pc.w_fwd = pc.w_dgrad = pc.bias = None
-            pc.key = key
         dt = _act_dtype(self.precision)
         tc = self._impl() == "tc"
-        if pc.w_fwd is None:
-            pc.w_fwd = ops.pack_weight(conv.weight, L.W_TC_FWD if tc else L.W_SIMT_FWD, dt)
-            pc.bias = ops.pad_bias(b, conv.out_channels, conv.weight.device)
-        if need_dgrad and pc.w_dgrad is None:
-            pc.w_dgrad = ops.pack_weight(conv.weight, L.W_TC_DGRAD if tc else L.W_SIMT_DGRAD, dt)
+        stale = pc.key != key
+        if stale and (pc.key is None or pc.key[3:] != key[3:] or pc.key[0] != key[0]):
+            pc.w_fwd = pc.w_dgrad = pc.bias = None      # different precision / shape / storage: new buffers
+        # same shape: re-pack INTO the existing buffers, so captured CUDA graphs stay valid
+        if pc.w_fwd is None or stale:
+            pc.w_fwd = ops.pack_weight(conv.weight, L.W_TC_FWD if tc else L.W_SIMT_FWD, dt, out=pc.w_fwd)
+            pc.bias = ops.pad_bias(b, conv.out_channels, conv.weight.device, out=pc.bias)
+        if (need_dgrad and pc.w_dgrad is None) or (stale and pc.w_dgrad is not None):
+            pc.w_dgrad = ops.pack_weight(conv.weight, L.W_TC_DGRAD if tc else L.W_SIMT_DGRAD, dt, out=pc.w_dgrad)
+        pc.key = key
         return pc
 
     def invalidate_packed(self) -> None:
@@ -169,10 +171,13 @@ class OSVOS_VGG(nn.Module):
         self._packed.clear()
         self._side_key = None
 
-    def _side(self) -> torch.Tensor:
+    def _side_cache_key(self):
         ps = [m.weight for m in self.upscale] + [m.weight for m in self.upscale_] + \
              [m.weight for m in self.score_dsn] + [m.bias for m in self.score_dsn] + [self.fuse.weight, self.fuse.bias]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def _side(self) -> torch.Tensor:
+        key = self._side_cache_key()
         if key != self._side_key:
             up_key = key[:4]
             if self._side_key is None or self._side_key[:4] != up_key:

@@ -1,117 +1,32 @@
 """One-shot online fine-tuning and per-sequence inference on one GPU.
 
 Mirrors the hot loops of the reference drivers, with the same argument meaning:
-  ``finetune``      <- ``train_online._train`` loop body (``src/train_online.py:75-101``)
-  ``infer_sequence``<- ``util/experiment_helper.test`` (``src/util/experiment_helper.py:34-64``)
-  ``sequences_for_rank`` <- the ``--sequence-group`` round-robin (``src/train_online.py:184-186``)
+  ``finetune`` / ``OnlineTrainer`` <- ``train_online._train`` loop body (``src/train_online.py:75-101``)
+  ``infer_sequence``               <- ``util/experiment_helper.test`` (``src/util/experiment_helper.py:34-64``)
+  ``sequences_for_rank``           <- the ``--sequence-group`` round-robin (``src/train_online.py:184-186``)
 
 Differences that do not change results: the frame/mask stay resident on the device (the
 reference re-uploads the same first frame every iteration, ``train_online.py:77``), the loss
 scalar stays on the device (the reference syncs every iteration, ``:82``), the optimizer step
-and ``zero_grad`` are one launch, and the whole micro-iteration can be replayed from a CUDA
-graph.
+and ``zero_grad`` are one launch, and the micro-iteration (forward, loss, backward) and the
+optimizer step (+ weight re-packing) are each replayed from a CUDA graph that is captured once per
+frame size and reused for every sequence the process handles.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
 from . import _lib as L
 from . import ops
-from .networks import OSVOS_VGG
+from .networks import OSVOS_VGG, _act_dtype
 from .optim import FusedSGD, get_optimizer_online
 
 
-class _MicroStep:
-    """fwd -> balanced loss (fused map, size_average=False) -> /n -> bwd into p.grad (+=)."""
-
-    def __init__(self, net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, avg_grad_every_n: int,
-                 deep_supervision: Optional[float] = None):
-        self.net, self.frame, self.mask = net, frame, mask
-        self.scale = 1.0 / float(avg_grad_every_n)
-        self.deep = deep_supervision      # None: online (fused map only); w: offline weight on the 4 side maps
-        self.names = net._grad_names()
-        params = dict(net.named_parameters())
-        self.grads: Dict[str, torch.Tensor] = {}
-        for n in self.names:
-            p = params[n]
-            if p.grad is None:
-                p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            self.grads[n] = p.grad
-        self.loss_sum = torch.zeros((), dtype=torch.float32, device=frame.device)
-        self.last_loss = torch.zeros((), dtype=torch.float32, device=frame.device)
-
-    def run(self) -> None:
-        outs, _, _, saved = self.net._run_forward(self.frame, save=True)
-        douts: List[Optional[torch.Tensor]] = [None] * 5
-        loss, stats = ops.bal_loss_fwd(outs[4], self.mask, False)
-        douts[4] = ops.bal_loss_bwd(outs[4], self.mask, False, stats, None, self.scale)
-        total = loss
-        if self.deep is not None:
-            for i in range(4):
-                li, st = ops.bal_loss_fwd(outs[i], self.mask, False)
-                douts[i] = ops.bal_loss_bwd(outs[i], self.mask, False, st, None, self.scale * self.deep)
-                total = total + self.deep * li
-        self.last_loss.copy_(total)
-        self.loss_sum.add_(total)
-        self.net._run_backward(saved, douts, self.grads)
-
-
-def finetune(net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, n_iters: int, avg_grad_every_n: int = 5,
-             optimizer: Optional[FusedSGD] = None, use_graph: bool = False,
-             losses_out: Optional[list] = None) -> torch.Tensor:
-    """Fine-tune ``net`` on one annotated frame (``train_online.py:70-101`` with a 1-sample loader).
-
-    frame (1,3,H,W) fp32, mask (1,1,H,W) fp32, both on the device.  Returns the device scalar of the
-    summed per-iteration losses (no host sync inside the loop unless ``losses_out`` is given)."""
-    L.require_device(frame.device)
-    if optimizer is None:
-        optimizer = get_optimizer_online(net)
-    frame = frame.contiguous().float()
-    mask = mask.contiguous().float()
-    micro = _MicroStep(net, frame, mask, avg_grad_every_n)
-    graph = None
-    if use_graph:
-        # warm up once outside capture (packs weights, sizes the allocator), then undo its gradient
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            calls0 = L.CALLS[0]
-            micro.run()
-            calls_per_replay = L.CALLS[0] - calls0
-            for g in micro.grads.values():
-                g.zero_()
-            micro.loss_sum.zero_()
-        torch.cuda.current_stream().wait_stream(s)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            micro.run()
-        for g in micro.grads.values():
-            g.zero_()
-        micro.loss_sum.zero_()
-    counter = 0
-    for _ in range(n_iters):
-        if graph is not None:
-            graph.replay()
-            L.CALLS[0] += calls_per_replay
-        else:
-            micro.run()
-        if losses_out is not None:
-            losses_out.append(float(micro.last_loss.item()))
-        counter += 1
-        if counter % avg_grad_every_n == 0:
-            optimizer.step_and_zero()
-            if graph is not None:
-                _repack_in_place(net)
-            counter = 0
-    return micro.loss_sum
-
-
 def _repack_in_place(net: OSVOS_VGG) -> None:
-    """Refresh the packed weight copies INTO their existing buffers (addresses are baked into a
-    captured graph) after an optimizer step."""
-    from .networks import _act_dtype
+    """Refresh the packed weight copies INTO their existing buffers (their addresses are baked into
+    captured graphs) after the parameters changed."""
     dt = _act_dtype(net.precision)
     tc = net._impl() == "tc"
     convs = [c for st in net._stage_convs() for c in st] + list(net.side_prep)
@@ -125,15 +40,201 @@ def _repack_in_place(net: OSVOS_VGG) -> None:
             ops.pad_bias(b, conv.out_channels, conv.weight.device, out=pc.bias)
         if pc.w_dgrad is not None:
             ops.pack_weight(conv.weight, L.W_TC_DGRAD if tc else L.W_SIMT_DGRAD, dt, out=pc.w_dgrad)
-        pc.key = (conv.weight.data_ptr(), conv.weight._version, None if b is None else (b.data_ptr(), b._version),
-                  net.precision, tuple(conv.weight.shape))
-    # fuse / score heads feed the side-chain parameter block
-    ops.side_params_prepare([m.weight for m in net.upscale], [m.weight for m in net.upscale_],
-                            [m.weight for m in net.score_dsn], [m.bias for m in net.score_dsn],
-                            net.fuse.weight, net.fuse.bias, out=net._side_params)
-    ps = [m.weight for m in net.upscale] + [m.weight for m in net.upscale_] + \
-         [m.weight for m in net.score_dsn] + [m.bias for m in net.score_dsn] + [net.fuse.weight, net.fuse.bias]
-    net._side_key = tuple((p.data_ptr(), p._version) for p in ps)
+    if net._side_params is not None:
+        ops.side_params_prepare([m.weight for m in net.upscale], [m.weight for m in net.upscale_],
+                                [m.weight for m in net.score_dsn], [m.bias for m in net.score_dsn],
+                                net.fuse.weight, net.fuse.bias, out=net._side_params)
+    _sync_cache_keys(net)
+
+
+def _sync_cache_keys(net: OSVOS_VGG) -> None:
+    """Mark the packed copies as current for the parameters' present versions."""
+    convs = [c for st in net._stage_convs() for c in st] + list(net.side_prep)
+    for conv in convs:
+        pc = net._packed.get(id(conv))
+        if pc is not None:
+            b = conv.bias
+            pc.key = (conv.weight.data_ptr(), conv.weight._version, None if b is None else (b.data_ptr(), b._version),
+                      net.precision, tuple(conv.weight.shape))
+    if net._side_params is not None:
+        net._side_key = net._side_cache_key()
+
+
+def _keys_current(net: OSVOS_VGG) -> bool:
+    convs = [c for st in net._stage_convs() for c in st] + list(net.side_prep)
+    for conv in convs:
+        pc = net._packed.get(id(conv))
+        if pc is not None and pc.key is not None:
+            b = conv.bias
+            if pc.key[1] != conv.weight._version or (b is not None and pc.key[2] != (b.data_ptr(), b._version)):
+                return False
+    return net._side_params is None or net._side_key == net._side_cache_key()
+
+
+class OnlineTrainer:
+    """The fine-tune loop of ``train_online._train`` for one frame size, reusable across sequences.
+
+    ``micro`` = fwd -> balanced loss on the fused map (size_average=False) -> / avg_grad_every_n ->
+    bwd accumulating into ``p.grad``;  every ``avg_grad_every_n`` micro-iterations:
+    ``optimizer.step(); optimizer.zero_grad()`` (one fused launch) and re-packing of the kernel-side
+    weight copies.  ``deep_supervision=w`` adds the four side-map losses with weight ``w``
+    (``train_offline.py:84-88``: ``w = 1 - epoch/n_epochs``).
+    """
+
+    def __init__(self, net: OSVOS_VGG, height: int, width: int, avg_grad_every_n: int = 5,
+                 optimizer: Optional[FusedSGD] = None, use_graph: bool = True, deep_supervision: Optional[float] = None):
+        dev = next(net.parameters()).device
+        L.require_device(dev)
+        self.net = net
+        self.n = int(avg_grad_every_n)
+        self.scale = 1.0 / float(avg_grad_every_n)
+        self.deep = deep_supervision
+        self.optimizer = optimizer if optimizer is not None else get_optimizer_online(net)
+        self.fused = isinstance(self.optimizer, FusedSGD)
+        self.use_graph = bool(use_graph) and self.fused
+        self.frame = torch.zeros((1, net.stages[0][0].in_channels, height, width), dtype=torch.float32, device=dev)
+        self.mask = torch.zeros((1, 1, height, width), dtype=torch.float32, device=dev)
+        params = dict(net.named_parameters())
+        self.grads: Dict[str, torch.Tensor] = {}
+        for name in net._grad_names():
+            p = params[name]
+            if p.grad is None:
+                p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            self.grads[name] = p.grad
+        self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+        self.last_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.counter = 0
+        self._micro_graph = None
+        self._step_graph = None
+        self._calls_micro = 0
+        self._calls_step = 0
+
+    # ---------------------------------------------------------------- pieces
+    def _micro(self) -> None:
+        net = self.net
+        outs, _, _, saved = net._run_forward(self.frame, save=True)
+        douts: List[Optional[torch.Tensor]] = [None] * 5
+        loss, stats = ops.bal_loss_fwd(outs[4], self.mask, False)
+        douts[4] = ops.bal_loss_bwd(outs[4], self.mask, False, stats, None, self.scale)
+        total = loss
+        if self.deep is not None:
+            for i in range(4):
+                li, st = ops.bal_loss_fwd(outs[i], self.mask, False)
+                douts[i] = ops.bal_loss_bwd(outs[i], self.mask, False, st, None, self.scale * self.deep)
+                total = total + self.deep * li
+        self.last_loss.copy_(total)
+        self.loss_sum.add_(total)
+        net._run_backward(saved, douts, self.grads)
+
+    def _step(self) -> None:
+        if self.fused:
+            self.optimizer.step_and_zero()
+            _repack_in_place(self.net)
+        else:
+            self.optimizer.step()
+            for g in self.grads.values():
+                g.zero_()
+
+    def _capture(self) -> None:
+        """Warm up once (packs weights, sizes the allocator), then capture both graphs."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            c0 = L.CALLS[0]
+            self._micro()
+            self._calls_micro = L.CALLS[0] - c0
+            for g in self.grads.values():
+                g.zero_()
+            self.optimizer._ensure_table()          # momentum buffers + device table exist before capture
+        torch.cuda.current_stream().wait_stream(s)
+        self._micro_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._micro_graph):
+            self._micro()
+        c0 = L.CALLS[0]
+        self._step_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._step_graph, pool=self._micro_graph.pool()):
+            self._step()
+        self._calls_step = L.CALLS[0] - c0
+        # capture does not execute: gradients are still zero, parameters untouched; versions were bumped
+        _sync_cache_keys(self.net)
+        self.loss_sum.zero_()
+
+    # ---------------------------------------------------------------- public
+    def reset(self, state_dict: Optional[dict] = None) -> None:
+        """Start a new sequence: (optionally) reload the parent weights in place
+        (``NetworkProvider.load_model``, network_provider.py:53-58), clear gradients and momentum."""
+        if state_dict is not None:
+            self.net.load_state_dict(state_dict)
+        for g in self.grads.values():
+            g.zero_()
+        for st in self.optimizer.state.values():
+            buf = st.get("momentum_buffer")
+            if buf is not None:
+                buf.zero_()
+        self.loss_sum.zero_()
+        self.counter = 0
+        if self.net._packed:
+            _repack_in_place(self.net)
+        if state_dict is not None and self.net._side_params is not None:
+            self.net._side_key = None          # new up-sampling weights: re-run the structure check (one sync,
+            self.net._side()                   # outside any graph) and rebuild the parameter block in place
+
+    def set_frame(self, frame: torch.Tensor, mask: torch.Tensor) -> None:
+        """Copy the annotated frame (1,3,H,W) and its mask (1,1,H,W) into the resident buffers
+        (host tensors are uploaded; pinned ones asynchronously)."""
+        self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)
+        self.mask.copy_(mask.reshape(self.mask.shape), non_blocking=True)
+
+    def run(self, n_iters: int, losses_out: Optional[list] = None) -> torch.Tensor:
+        if self.use_graph and self._micro_graph is None:
+            self._capture()
+        elif self.use_graph and not _keys_current(self.net):
+            _repack_in_place(self.net)          # parameters were changed from outside since the last replay
+        for _ in range(n_iters):
+            if self.use_graph:
+                self._micro_graph.replay()
+                L.CALLS[0] += self._calls_micro
+            else:
+                self._micro()
+            if losses_out is not None:
+                losses_out.append(float(self.last_loss.item()))
+            self.counter += 1
+            if self.counter % self.n == 0:
+                if self.use_graph:
+                    self._step_graph.replay()
+                    L.CALLS[0] += self._calls_step
+                    for p in self.net.parameters():
+                        torch.autograd.graph.increment_version(p)
+                    _sync_cache_keys(self.net)
+                else:
+                    self._step()
+                self.counter = 0
+        return self.loss_sum
+
+
+def finetune(net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, n_iters: int, avg_grad_every_n: int = 5,
+             optimizer: Optional[FusedSGD] = None, use_graph: bool = False,
+             losses_out: Optional[list] = None) -> torch.Tensor:
+    """Fine-tune ``net`` on one annotated frame (``train_online.py:70-101`` with a 1-sample loader).
+
+    frame (1,3,H,W) fp32, mask (1,1,H,W) fp32.  Returns the device scalar of the summed
+    per-iteration losses (no host sync inside the loop unless ``losses_out`` is given).  The trainer
+    (and its CUDA graphs) is cached on ``net`` per frame size, so later calls replay."""
+    L.require_device(next(net.parameters()).device)
+    key = (int(frame.shape[-2]), int(frame.shape[-1]), int(avg_grad_every_n), bool(use_graph), id(optimizer), net.precision)
+    cache = net.__dict__.setdefault("_trainers", {})
+    tr = cache.get(key)
+    if tr is None:
+        cache.clear()                           # one resident trainer per net: graphs pin a lot of memory
+        tr = OnlineTrainer(net, key[0], key[1], avg_grad_every_n, optimizer, use_graph)
+        cache[key] = tr
+    elif optimizer is None:
+        tr.reset()                              # a fresh optimizer per call, like get_optimizer() per sequence
+    else:
+        tr.loss_sum.zero_()
+        tr.counter = 0
+    tr.set_frame(frame, mask)
+    return tr.run(n_iters, losses_out)
 
 
 @torch.no_grad()
@@ -141,10 +242,14 @@ def infer_sequence(net: OSVOS_VGG, frames: torch.Tensor, batch_size: int = 1, wa
     """Segment every frame of a sequence (``experiment_helper.test``'s loop): returns uint8 masks
     (F,1,H,W) [and fp32 probabilities] on the device; sigmoid + threshold are fused into the
     side-chain kernel instead of a host-side numpy pass (``experiment_helper.py:55-57``)."""
-    L.require_device(frames.device)
+    dev = next(net.parameters()).device
+    L.require_device(dev)
     masks, probs = [], []
     for i in range(0, frames.shape[0], batch_size):
-        _, prob, mask = net.predict(frames[i:i + batch_size])
+        fb = frames[i:i + batch_size]
+        if fb.device != dev:
+            fb = fb.to(dev, non_blocking=True)
+        _, prob, mask = net.predict(fb)
         masks.append(mask)
         if want_prob:
             probs.append(prob)

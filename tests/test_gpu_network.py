@@ -186,6 +186,39 @@ def test_finetune_variants_track_golden(precision, use_graph):
     assert float((torch.sigmoid(fused) - torch.sigmoid(ft["fused_after"])).abs().max()) <= _tol(precision, "random")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_trainer_graph_is_reused_across_sequences(precision):
+    """One resident OnlineTrainer (captured graphs) serves consecutive sequences: after reset() with the
+    parent weights the second run reproduces the first, and matches the golden trajectory."""
+    from fosvos_b200.online import OnlineTrainer
+    fix = _load("fwd_48x72_random.pt")
+    x, m, sd = _case(fix)
+    ft = fix["finetune"]
+    net = _net(sd, precision)
+    tr = OnlineTrainer(net, fix["H"], fix["W"], ft["avg_grad_every_n"], FB.get_optimizer_online(net, learning_rate=ft["learning_rate"]),
+                       use_graph=True)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    runs = []
+    for seq in range(3):
+        tr.reset(sd_dev)
+        if seq == 1:                                      # a different frame in between must not leak state
+            x2, m2 = synth.make_frame(9, 0, fix["H"], fix["W"], noise=True)
+            tr.set_frame(x2, m2)
+        else:
+            tr.set_frame(x.to(DEV), m.to(DEV))
+        losses = []
+        tr.run(ft["n_iters"], losses_out=losses)
+        runs.append(losses)
+    rt = 2e-4 if precision == "fp32" else 5e-2
+    assert np.allclose(runs[0], ft["losses"], rtol=rt), (runs[0], ft["losses"])
+    assert np.allclose(runs[2], runs[0], rtol=1e-5 if precision == "fp32" else 2e-3), (runs[0], runs[2])
+    assert not np.allclose(runs[1], runs[0], rtol=1e-3)
+    # inference after fine-tuning uses the updated weights (packed copies are refreshed in place)
+    with torch.no_grad():
+        fused = net(x.to(DEV))[-1].cpu()
+    assert float((torch.sigmoid(fused) - torch.sigmoid(ft["fused_after"])).abs().max()) <= _tol(precision, "random")
+
+
 def test_autograd_path_with_torch_sgd_matches_fused_trainer():
     """Reference-style loop (autograd + optimizer.step/zero_grad, train_online.py:75-101) on the
     drop-in module == the fused trainer."""
