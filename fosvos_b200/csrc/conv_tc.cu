@@ -19,6 +19,7 @@
 // elected thread), warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/mask/accumulate -> bf16
 // NHWC global stores).  The same kernel computes the data gradient (weights packed flipped and
 // transposed, epilogue = ReLU mask [+ accumulate]).
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -31,13 +32,18 @@ constexpr int TC_BM = 128;       // pixels per tile
 constexpr int TC_BK = 64;        // channels per K slab (128 B of bf16 = one swizzle row)
 constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+// diagnostic flag bits (tools/conv_probe.py): drop one pipeline component to see what bounds a layer
+constexpr int DBG_SKIP_A = 1 << 16, DBG_SKIP_B = 1 << 17, DBG_SKIP_STORE = 1 << 18, DBG_SKIP_MMA = 1 << 19;
 
 template <int BN> struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  // BN >= 64: the epilogue stages 64-channel output slabs (128 px x 128 B, SWIZZLE_128B) in two 16 KB buffers for TMA stores
+  static constexpr bool STAGED = BN >= 64;
+  static constexpr int STAGING_BYTES = STAGED ? 2 * TC_A_BYTES : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
 struct TcParams {
@@ -54,23 +60,29 @@ struct TcParams {
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ CUtensorMap map_y, const TcParams p) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then treats the role branches as warp-uniform and keeps the
+  // descriptors / barrier addresses of the single-thread issue loops in uniform registers (a `lane == 0` branch
+  // costs ~2x in tcgen05.mma issue rate: tools/exp/mma_issue.cu)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
     ptx::prefetch_tensormap(&map_w);
+    if (Cfg::STAGED) ptx::prefetch_tensormap(&map_y);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -91,8 +103,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -108,16 +120,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + TC_A_BYTES;
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          ptx::tma_load_4d(a_dst, &map_x, &full_bar[stage], chunk * TC_BK, x0 + s - 1, y0 + r - 1, n);
-          ptx::tma_load_2d(b_dst, &map_w, &full_bar[stage], tap * p.cin_pad + chunk * TC_BK, n0);
+          if (ptx::elect_one()) {
+            const bool la = !(p.flags & DBG_SKIP_A), lb = !(p.flags & DBG_SKIP_B);
+            if (la || lb) ptx::mbar_expect_tx(&full_bar[stage], (la ? TC_A_BYTES : 0) + (lb ? Cfg::B_BYTES : 0));
+            else ptx::mbar_arrive(&full_bar[stage]);
+            if (la) ptx::tma_load_4d(a_dst, &map_x, &full_bar[stage], chunk * TC_BK, x0 + s - 1, y0 + r - 1, n);
+            if (lb) ptx::tma_load_2d(b_dst, &map_w, &full_bar[stage], tap * p.cin_pad + chunk * TC_BK, n0);
+          }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -134,15 +151,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
           const uint64_t da = ptx::umma_desc_sw128_kmajor(a_addr);
           const uint64_t db = ptx::umma_desc_sw128_kmajor(a_addr + TC_A_BYTES);
+          if (ptx::elect_one()) {
+            if (!(p.flags & DBG_SKIP_MMA)) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+                ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              }
+            }
+            ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+            if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
           }
-          ptx::umma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[as]);                 // accumulator complete -> epilogue
       }
     }
   } else {
@@ -150,14 +172,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;                     // accumulator row = pixel inside the patch
     const int py = row >> p.tw_shift, px = row & (TW - 1);
+    const bool issuer = (warp == 2) && (lane == 0);       // owns the TMA-store bulk groups
     int it = 0;
+    uint32_t slab_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.n_tiles_n;
       int m = tile / p.n_tiles_n;
       const int tx = m % p.tiles_x; m /= p.tiles_x;
       const int ty = m % p.tiles_y;
       const int n = m / p.tiles_y;
-      const int gx = tx * TW + px, gy = ty * TH + py, n0 = nt * BN;
+      const int x0 = tx * TW, y0 = ty * TH;
+      const int gx = x0 + px, gy = y0 + py, n0 = nt * BN;
       const bool in_img = gx < p.W && gy < p.H;
       const long long pix = ((long long)n * p.H + gy) * p.W + gx;
       const int as = it & 1;
@@ -165,45 +190,125 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      if constexpr (Cfg::STAGED) {
+        // 64-channel slabs: TMEM -> registers -> bias/ReLU/mask/accumulate -> bf16 -> swizzled smem -> one TMA store
+        // (the store clips the patch at the frame edge and the channel tail)
+        constexpr int SLABS = BN / 64;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld16(taddr + c0, r);
-        ptx::tmem_ld_wait();
-        if (in_img) {
+        for (int j = 0; j < SLABS; ++j) {
+          const int co0 = n0 + 64 * j;
+          const bool live = co0 < p.CoutP;                // uniform: N-tail tiles have dead slabs
+          uint32_t packed[32];
+          if (live) {
+            uint32_t r[64];
+            ptx::tmem_ld32(taddr + 64 * j, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            ptx::tmem_ld32(taddr + 64 * j + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int co = n0 + c0 + 8 * h;
-            if (co < p.CoutP) {
+            for (int h = 0; h < 8; ++h) {
+              const int co = co0 + 8 * h;
               float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[j] = __uint_as_float(r[8 * h + j]);
-                if (p.flags & FOSVOS_CONV_BIAS) v[j] += __ldg(p.bias + co + j);
-                if (p.flags & FOSVOS_CONV_RELU) v[j] = fmaxf(v[j], 0.f);
-              }
-              const long long o = pix * p.CoutP + co;
-              if (p.flags & FOSVOS_CONV_MASK) {
-                float mk[8];
-                load8(p.mask + o, mk);
+              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[8 * h + q]);
+              if (co < p.CoutP) {
+                if (p.flags & FOSVOS_CONV_BIAS) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                if (p.flags & FOSVOS_CONV_RELU) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = mk[j] > 0.f ? v[j] : 0.f;
-              }
-              if (p.flags & FOSVOS_CONV_ACCUMULATE) {
-                float old[8];
-                load8(p.y + o, old);
+                  for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+                }
+                if ((p.flags & (FOSVOS_CONV_MASK | FOSVOS_CONV_ACCUMULATE)) && in_img) {
+                  const long long o = pix * p.CoutP + co;
+                  if (p.flags & FOSVOS_CONV_MASK) {
+                    float mk[8];
+                    load8(p.mask + o, mk);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += old[j];
+                    for (int q = 0; q < 8; ++q) v[q] = mk[q] > 0.f ? v[q] : 0.f;
+                  }
+                  if (p.flags & FOSVOS_CONV_ACCUMULATE) {
+                    float old[8];
+                    load8(p.y + o, old);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += old[q];
+                  }
+                }
               }
-              store8(p.y + o, v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                packed[4 * h + q] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+            }
+          }
+          if (j == SLABS - 1) {                           // all TMEM reads of this tile are done: hand the accumulator back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+          }
+          if (live) {
+            uint8_t* buf = staging + (slab_ctr & 1) * TC_A_BYTES;
+            if (issuer) ptx::tma_store_wait_read<1>();    // the store that used this buffer two slabs ago has read it
+            ptx::named_bar_sync(1, 128);
+            uint8_t* rowp = buf + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) =
+                  make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(2, 128);
+            if (issuer && !(p.flags & DBG_SKIP_STORE)) {
+              ptx::tma_store_4d(&map_y, buf, co0, x0, y0, n);
+              ptx::tma_store_commit();
+            }
+            ++slab_ctr;
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld16(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          if (in_img && !(p.flags & DBG_SKIP_STORE)) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int co = n0 + c0 + 8 * h;
+              if (co < p.CoutP) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  v[q] = __uint_as_float(r[8 * h + q]);
+                  if (p.flags & FOSVOS_CONV_BIAS) v[q] += __ldg(p.bias + co + q);
+                  if (p.flags & FOSVOS_CONV_RELU) v[q] = fmaxf(v[q], 0.f);
+                }
+                const long long o = pix * p.CoutP + co;
+                if (p.flags & FOSVOS_CONV_MASK) {
+                  float mk[8];
+                  load8(p.mask + o, mk);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) v[q] = mk[q] > 0.f ? v[q] : 0.f;
+                }
+                if (p.flags & FOSVOS_CONV_ACCUMULATE) {
+                  float old[8];
+                  load8(p.y + o, old);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) v[q] += old[q];
+                }
+                store8(p.y + o, v);
+              }
             }
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
     }
+    if (Cfg::STAGED && issuer) ptx::tma_store_wait_all<0>();   // shared memory must outlive the bulk reads
   }
 
   ptx::tc_fence_before();
@@ -275,7 +380,7 @@ static int pick_tw_shift(int H, int W) {
 }
 
 template <int BN>
-static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -283,8 +388,9 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
     attr_set = true;
   }
-  const int grid = min(p.total_tiles, num_sms());
-  conv3x3_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
+  int grid = min(p.total_tiles, num_sms());
+  if (const char* e = getenv("FOSVOS_TC_GRID")) { const int v = atoi(e); if (v > 0) grid = min(grid, v); }
+  conv3x3_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, my, p);
   return check_launch("conv3x3_tc");
 }
 
@@ -320,22 +426,25 @@ int fosvos_conv3x3_tc(const void* x, const void* w_packed, const float* bias, co
   // small grids: prefer narrower N tiles so that more SMs get work
   const long long m_tiles = (long long)N * p.tiles_x * p.tiles_y;
   while (BN > 64 && m_tiles * ceil_div(Cout, BN) < num_sms()) BN /= 2;
+  if (const char* e = getenv("FOSVOS_TC_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && (v & (v - 1)) == 0) BN = v; }
   p.n_tiles_n = ceil_div(Cout, BN);
   FOSVOS_REQUIRE(m_tiles * p.n_tiles_n < (1LL << 31), "conv3x3_tc: too many tiles");
   p.total_tiles = (int)(m_tiles * p.n_tiles_n);
 
-  CUtensorMap mx, mw;
+  CUtensorMap mx, mw, my;
   int rc = encode_act_map(&mx, x, N, H, W, Cin, TW, TH);
+  if (rc) return rc;
+  rc = encode_act_map(&my, y, N, H, W, Cout, TW, TH);      // output slabs leave through TMA stores (BN >= 64)
   if (rc) return rc;
   rc = encode_w_map(&mw, w_packed, Cout, 9 * p.cin_pad, BN);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   switch (BN) {
-    case 16: return launch_tc<16>(mx, mw, p, st);
-    case 32: return launch_tc<32>(mx, mw, p, st);
-    case 64: return launch_tc<64>(mx, mw, p, st);
-    case 128: return launch_tc<128>(mx, mw, p, st);
-    default: return launch_tc<256>(mx, mw, p, st);
+    case 16: return launch_tc<16>(mx, mw, my, p, st);
+    case 32: return launch_tc<32>(mx, mw, my, p, st);
+    case 64: return launch_tc<64>(mx, mw, my, p, st);
+    case 128: return launch_tc<128>(mx, mw, my, p, st);
+    default: return launch_tc<256>(mx, mw, my, p, st);
   }
 }
 

@@ -65,7 +65,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   uint64_t* done_bar = empty_bar + p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform roles
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
     ptx::prefetch_tensormap(&map_z);
@@ -101,7 +101,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const int z_off = p.x_is_a ? p.a_bytes : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = p_begin; pt < p_end; ++pt) {
@@ -112,16 +112,19 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int x0 = tx * TW, y0 = ty * TH;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * p.stage_bytes;
-        ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
-        for (int j = 0; j < nb_x; ++j)
-          ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], xc0 + 64 * j, x0 + s - 1, y0 - 1, n);
-        for (int j = 0; j < nb_z; ++j)
-          ptx::tma_load_4d(st + z_off + j * WG_PLAIN_BLOCK, &map_z, &full_bar[stage], zc0 + 64 * j, x0, y0, n);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+          for (int j = 0; j < nb_x; ++j)
+            ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], xc0 + 64 * j, x0 + s - 1, y0 - 1, n);
+          for (int j = 0; j < nb_z; ++j)
+            ptx::tma_load_4d(st + z_off + j * WG_PLAIN_BLOCK, &map_z, &full_bar[stage], zc0 + 64 * j, x0, y0, n);
+        }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // kind::f16, D fp32, A/B bf16, both MN-major (bits 15/16), M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -135,6 +138,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         ptx::tc_fence_after();
         const uint32_t st = ptx::smem_u32(smem + stage * p.stage_bytes);
         const uint32_t a_base = st, b_base = st + p.a_bytes;
+        if (ptx::elect_one()) {
 #pragma unroll 1
         for (int r = 0; r < 3; ++r) {
           const uint32_t a_r = a_base + (p.x_is_a ? r * tap_bytes : 0);
@@ -147,9 +151,11 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           }
         }
         ptx::umma_commit(&empty_bar[stage]);
+        if (pt == p_end - 1) ptx::umma_commit(done_bar);
+        }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(done_bar);
     }
   } else {
     // ===================== epilogue: TMEM -> vectorised fp32 reductions =====================

@@ -145,7 +145,7 @@ class OSVOS_VGG(nn.Module):
     def _wgrad_impl(self, cin_p: int) -> str:
         # the tensor-core weight gradient needs a reasonably filled 64-channel K-slab of X; the 3-channel
         # first layer (padded to 8) stays on the direct kernel
-        return "tc" if (self._impl() == "tc" and cin_p >= 32) else "simt"
+        return "tc" if (self._impl() == "tc" and cin_p >= 8) else "simt"
 
     def _packed_for(self, conv: nn.Conv2d, need_dgrad: bool) -> _PackedConv:
         pc = self._packed.setdefault(id(conv), _PackedConv())

@@ -1,0 +1,52 @@
+"""Time the tcgen05 weight-gradient kernel per layer shape; check the Cin=3 (padded 8) case against the direct kernel."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from fosvos_b200 import ops
+
+dev = torch.device("cuda:0")
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+LAYERS = [(480, 854, 3, 64), (480, 854, 64, 64), (240, 427, 64, 128), (240, 427, 128, 128), (240, 427, 128, 16),
+          (120, 214, 128, 256), (120, 214, 256, 256), (120, 214, 256, 16), (60, 107, 256, 512), (60, 107, 512, 512),
+          (60, 107, 512, 16), (30, 54, 512, 512), (30, 54, 512, 16)]
+
+
+def timeit(fn, reps=10):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+for (h, w, cin, cout) in LAYERS:
+    cinp = ops.pad8(cin)
+    x = torch.randn((batch, h, w, cinp), device=dev).to(torch.bfloat16)
+    if cinp != cin:
+        x[..., cin:] = 0
+    dz = (torch.randn((batch, h, w, cout), device=dev) * 0.1).to(torch.bfloat16)
+    flops = 2.0 * batch * h * w * cin * cout * 9
+    msg = f"{h}x{w} {cin}->{cout}:"
+    res = {}
+    for impl in ("tc", "simt") if cin == 3 else ("tc",):
+        dw = torch.zeros((cout, cin, 3, 3), device=dev)
+        db = torch.zeros(cout, device=dev)
+        ops.conv3x3_wgrad(x, dz, dw, db, impl=impl)
+        torch.cuda.synchronize()
+        res[impl] = (dw.clone(), db.clone())
+        t = timeit(lambda: ops.conv3x3_wgrad(x, dz, dw, db, impl=impl))
+        t2 = timeit(lambda: ops.conv3x3_wgrad(x, dz, dw, None, impl=impl))
+        msg += f" {impl}={t:.1f}us ({flops / t / 1e6:.0f}TF) nobias={t2:.1f}us"
+    if len(res) == 2:
+        d = (res["tc"][0] - res["simt"][0]).abs().max().item()
+        s = res["simt"][0].abs().max().item()
+        msg += f" | tc-vs-simt max|d|={d:.3e} scale={s:.3e} db d={(res['tc'][1] - res['simt'][1]).abs().max().item():.3e}"
+    print(msg, flush=True)
