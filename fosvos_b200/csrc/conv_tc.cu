@@ -1,10 +1,10 @@
-// 3x3 convolution (stride 1, pad 1) as an implicit GEMM on the 5th-generation tensor cores.
+// 3x3 (and 1x1) convolution, stride 1, as an implicit GEMM on the 5th-generation tensor cores.
 //
 //   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[cout, tap, cin]        bf16 x bf16 -> fp32
 //
 //   GEMM-M = 128 output pixels: a TH x TW spatial patch of one frame (TH*TW = 128)
 //   GEMM-N = BN output channels (16..256)
-//   GEMM-K = 9 taps x Cin, walked in (tap, 64-channel) slabs
+//   GEMM-K = taps x Cin, walked in (tap, 64-channel) slabs
 //
 // A operand: the NHWC activation tensor is described to TMA as a 4-D tensor (C, W, H, N); the slab
 // for tap (r,s) is the box {64, TW, TH, 1} at (c0, x0+s-1, y0+r-1, n).  Out-of-bounds elements are
@@ -15,13 +15,22 @@
 // Accumulators live in TMEM (2 stages x BN columns) so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Persistent CTAs, one per SM, static round-robin over tiles.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
-// elected thread), warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/mask/accumulate -> bf16
-// NHWC global stores).  The same kernel computes the data gradient (weights packed flipped and
-// transposed, epilogue = ReLU mask [+ accumulate]).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 =
+// two epilogue groups of four warps (group g drains accumulator stage g, i.e. every other tile):
+// TMEM -> registers -> bias/ReLU/mask/accumulate -> bf16 -> swizzled shared-memory slab -> TMA store
+// (which also clips the patch at the frame edge).  The role branches are warp-uniform and the single
+// issuing lane is picked with elect.sync, so descriptors stay in uniform registers (a `lane == 0` branch
+// halves the tcgen05.mma issue rate; tools/exp/mma_issue.cu).
+// The same kernel computes the data gradient (weights packed flipped and transposed, epilogue = ReLU
+// mask [+ accumulate]).
+//
+// MODE_C8 serves the first layer (Cin <= 8, e.g. the 3-channel frame padded to 8): all nine taps of a
+// patch are one pipeline stage of nine {8ch, TW, TH} boxes in the un-swizzled K-major core-matrix
+// layout (tap = one 16-byte K core matrix), the whole 64 x 80 weight stays resident in shared
+// memory, and a tile is five K=16 MMAs instead of 36 mostly-zero ones.
 #include <stdlib.h>
+
 #include <mutex>
-#include <unordered_map>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -30,58 +39,74 @@ namespace fosvos {
 
 constexpr int TC_BM = 128;       // pixels per tile
 constexpr int TC_BK = 64;        // channels per K slab (128 B of bf16 = one swizzle row)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
-// diagnostic flag bits (tools/conv_probe.py): drop one pipeline component to see what bounds a layer
-constexpr int DBG_SKIP_A = 1 << 16, DBG_SKIP_B = 1 << 17, DBG_SKIP_STORE = 1 << 18, DBG_SKIP_MMA = 1 << 19;
+constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one 64-channel output slab of a tile
+constexpr int MODE_GENERIC = 0, MODE_C8 = 1;
+constexpr int C8_TAP_BYTES = TC_BM * 16;         // 128 pixels x 8 channels
+constexpr int C8_KBLOCKS = 10;                   // 9 taps + 1 zero-weight pad -> 5 MMAs of K = 16
+constexpr int C8_W_BYTES = C8_KBLOCKS * 64 * 16; // [k block][64 couts][8 ch]
 
-template <int BN> struct TcCfg {
-  static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+template <int BN, int MODE> struct TcCfg {
+  static constexpr int A_BYTES = MODE == MODE_C8 ? C8_KBLOCKS * C8_TAP_BYTES : TC_A_BYTES;
+  static constexpr int B_BYTES = MODE == MODE_C8 ? 0 : BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = MODE == MODE_C8 ? 6 : (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
-  // BN >= 64: the epilogue stages 64-channel output slabs (128 px x 128 B, SWIZZLE_128B) in two 16 KB buffers for TMA stores
+  // BN >= 64: each epilogue group stages 64-channel output slabs (128 px x 128 B, SWIZZLE_128B) for TMA stores
   static constexpr bool STAGED = BN >= 64;
-  static constexpr int STAGING_BYTES = STAGED ? 2 * TC_A_BYTES : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int STAGING_BYTES = STAGED ? 2 * TC_SLAB_BYTES : 0;
+  static constexpr int WRES_BYTES = MODE == MODE_C8 ? C8_W_BYTES : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + WRES_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
 struct TcParams {
   const float* bias;             // CoutP fp32 or null
   const __nv_bfloat16* mask;     // (N,H,W,CoutP) or null
   __nv_bfloat16* y;              // (N,H,W,CoutP)
+  const __nv_bfloat16* w;        // packed weight (MODE_C8 reads it directly)
   int N, H, W, CoutP;
   int tiles_x, tiles_y, n_tiles_n, total_tiles;
   int tw_shift;                  // TW = 1 << tw_shift, TH = 128 >> tw_shift
   int k_chunks;                  // ceil(CinP / 64)
   int cin_pad;                   // k_chunks * 64: per-tap K extent of the packed weight
+  int taps;                      // 9 (3x3, pad 1) or 1 (1x1)
   int flags;
 };
 
-template <int BN>
+// Un-swizzled K-major operand: 8-row x 16-byte core matrices; `lbo` = byte distance between the two K core
+// matrices of one K=16 step, `sbo` = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_noswizzle_kmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_y, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MODE>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  uint8_t* wres = staging + Cfg::STAGING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wres + Cfg::WRES_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  // warp index through a shuffle: the compiler then treats the role branches as warp-uniform and keeps the
-  // descriptors / barrier addresses of the single-thread issue loops in uniform registers (a `lane == 0` branch
-  // costs ~2x in tcgen05.mma issue rate: tools/exp/mma_issue.cu)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
-    ptx::prefetch_tensormap(&map_w);
+    if (MODE != MODE_C8) ptx::prefetch_tensormap(&map_w);
     if (Cfg::STAGED) ptx::prefetch_tensormap(&map_y);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
@@ -89,93 +114,150 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 4);     // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[i], 4);     // one arrive per warp of the epilogue group
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  // everything above overlaps the tail of the previous kernel under programmatic dependent launch; global
+  // memory is only touched after the wait
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
+  if constexpr (MODE == MODE_C8) {
+    // resident weight image [k block][64 couts][8 ch] from the packed [cout][tap][64] layout; block 9 and dead couts = 0
+    for (int i = threadIdx.x; i < C8_KBLOCKS * 64; i += TC_THREADS) {
+      const int kb = i >> 6, co = i & 63;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (kb < 9 && co < p.CoutP) v = __ldg(reinterpret_cast<const uint4*>(p.w + ((long long)co * 9 + kb) * 64));
+      *reinterpret_cast<uint4*>(wres + i * 16) = v;
+    }
+    ptx::fence_proxy_async_smem();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_kb = 9 * p.k_chunks;
+  const int num_kb = p.taps * p.k_chunks;
   const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
-    {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        int m = tile / p.n_tiles_n;
-        const int tx = m % p.tiles_x; m /= p.tiles_x;
-        const int ty = m % p.tiles_y;
-        const int n = m / p.tiles_y;
-        const int x0 = tx * TW, y0 = ty * TH, n0 = nt * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.k_chunks, chunk = kb - tap * p.k_chunks;
-          const int r = tap / 3, s = tap - 3 * r;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + TC_A_BYTES;
-          if (ptx::elect_one()) {
-            const bool la = !(p.flags & DBG_SKIP_A), lb = !(p.flags & DBG_SKIP_B);
-            if (la || lb) ptx::mbar_expect_tx(&full_bar[stage], (la ? TC_A_BYTES : 0) + (lb ? Cfg::B_BYTES : 0));
-            else ptx::mbar_arrive(&full_bar[stage]);
-            if (la) ptx::tma_load_4d(a_dst, &map_x, &full_bar[stage], chunk * TC_BK, x0 + s - 1, y0 + r - 1, n);
-            if (lb) ptx::tma_load_2d(b_dst, &map_w, &full_bar[stage], tap * p.cin_pad + chunk * TC_BK, n0);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tiles_a = ptx::smem_u32(tiles), full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
+    uint32_t a_dst = tiles_a, bar_full = full_a, bar_empty = empty_a;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int m = tile / p.n_tiles_n;
+      const int tx = m % p.tiles_x; m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int n = m / p.tiles_y;
+      const int x0 = tx * TW, y0 = ty * TH, n0 = nt * BN;
+      if constexpr (MODE == MODE_C8) {
+        ptx::mbar_wait_a(bar_empty, phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx_a(bar_full, Cfg::A_BYTES);
+#pragma unroll
+          for (int t = 0; t < C8_KBLOCKS; ++t) {
+            const int tap = t < 9 ? t : 8;            // block 9 multiplies zero weights: any finite data will do
+            const int r = tap / 3, s = tap - 3 * r;
+            ptx::tma_load_4d_a(a_dst + t * C8_TAP_BYTES, &map_x, bar_full, 0, x0 + s - 1, y0 + r - 1, n);
           }
-          __syncwarp();
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        __syncwarp();
+        a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_dst = tiles_a; bar_full = full_a; bar_empty = empty_a; }
+      } else {
+        // taps outer, 64-channel chunks inner; no divisions and only running shared-memory addresses in the loop
+        const int n_r = p.taps == 9 ? 3 : 1;
+        int wk = 0;                                       // K coordinate in the packed weight: tap * cin_pad + chunk * 64
+        for (int r = 0; r < n_r; ++r) {
+          const int yy = p.taps == 9 ? y0 + r - 1 : y0;
+          for (int s = 0; s < n_r; ++s) {
+            const int xx = p.taps == 9 ? x0 + s - 1 : x0;
+            for (int c = 0; c < p.cin_pad; c += TC_BK, wk += TC_BK) {
+              ptx::mbar_wait_a(bar_empty, phase ^ 1);
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx_a(bar_full, Cfg::STAGE_BYTES);
+                ptx::tma_load_4d_a(a_dst, &map_x, bar_full, c, xx, yy, n);
+                ptx::tma_load_2d_a(a_dst + Cfg::A_BYTES, &map_w, bar_full, wk, n0);
+              }
+              __syncwarp();
+              a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_dst = tiles_a; bar_full = full_a; bar_empty = empty_a; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);      // epilogue has drained this accumulator
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    // SWIZZLE_128B K-major descriptor: low word = start address >> 4 | LBO(1) << 16, high word constant
+    const uint64_t desc0 = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(tiles));
+    const uint32_t a_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
+    const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
+    uint32_t a_lo = a_lo0, bar_full = full_a, bar_empty = empty_a;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);      // the epilogue group has drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      if constexpr (MODE == MODE_C8) {
+        ptx::mbar_wait_a(bar_full, phase);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);        // TMA bytes have landed
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = ptx::umma_desc_sw128_kmajor(a_addr);
-          const uint64_t db = ptx::umma_desc_sw128_kmajor(a_addr + TC_A_BYTES);
-          if (ptx::elect_one()) {
-            if (!(p.flags & DBG_SKIP_MMA)) {
+        const uint32_t a_addr = ptx::smem_u32(tiles) + stage * Cfg::STAGE_BYTES;
+        const uint32_t w_addr = ptx::smem_u32(wres);
+        if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) {
-                // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-                ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-              }
+          for (int j = 0; j < C8_KBLOCKS / 2; ++j) {
+            const uint64_t da = umma_desc_noswizzle_kmajor(a_addr + 2 * j * C8_TAP_BYTES, C8_TAP_BYTES, 128);
+            const uint64_t db = umma_desc_noswizzle_kmajor(w_addr + 2 * j * 64 * 16, 64 * 16, 128);
+            ptx::umma_bf16(tmem_d, da, db, idesc, j != 0);
+          }
+          ptx::umma_commit_a(bar_empty);
+          ptx::umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        bar_full += 8; bar_empty += 8;
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; bar_full = full_a; bar_empty = empty_a; }
+      } else {
+        const uint32_t tfull = ptx::smem_u32(&tmem_full[as]);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait_a(bar_full, phase);              // TMA bytes have landed
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+              ptx::umma_bf16_lohi(tmem_d, a_lo + 2 * k, a_lo + (Cfg::A_BYTES >> 4) + 2 * k, desc_hi, idesc, (kb | k) != 0);
             }
-            ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
-            if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+            ptx::umma_commit_a(bar_empty);                // frees the smem slot when the MMAs retire
+            if (kb == num_kb - 1) ptx::umma_commit_a(tfull);   // accumulator complete -> epilogue
           }
           __syncwarp();
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          a_lo += Cfg::STAGE_BYTES >> 4; bar_full += 8; bar_empty += 8;
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; bar_full = full_a; bar_empty = empty_a; }
         }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue: group g = warps 2+4g .. 5+4g drains accumulator stage g =====================
+    const int grp = (warp - 2) >> 2;
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;                     // accumulator row = pixel inside the patch
     const int py = row >> p.tw_shift, px = row & (TW - 1);
-    const bool issuer = (warp == 2) && (lane == 0);       // owns the TMA-store bulk groups
-    int it = 0;
-    uint32_t slab_ctr = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const bool issuer = (warp == 2 + 4 * grp) && (lane == 0);   // owns this group's TMA-store bulk groups
+    const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+    uint8_t* buf = staging + grp * TC_SLAB_BYTES;
+    const int as = grp;
+    int it = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int nt = tile % p.n_tiles_n;
       int m = tile / p.n_tiles_n;
       const int tx = m % p.tiles_x; m /= p.tiles_x;
@@ -185,7 +267,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       const int gx = x0 + px, gy = y0 + py, n0 = nt * BN;
       const bool in_img = gx < p.W && gy < p.H;
       const long long pix = ((long long)n * p.H + gy) * p.W + gx;
-      const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
@@ -250,21 +331,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
           }
           if (live) {
-            uint8_t* buf = staging + (slab_ctr & 1) * TC_A_BYTES;
-            if (issuer) ptx::tma_store_wait_read<1>();    // the store that used this buffer two slabs ago has read it
-            ptx::named_bar_sync(1, 128);
+            if (issuer) ptx::tma_store_wait_read<0>();    // the previous store of this group has read the buffer
+            ptx::named_bar_sync(bar_a, 128);
             uint8_t* rowp = buf + row * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) =
                   make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
             ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(2, 128);
-            if (issuer && !(p.flags & DBG_SKIP_STORE)) {
+            ptx::named_bar_sync(bar_b, 128);
+            if (issuer) {
               ptx::tma_store_4d(&map_y, buf, co0, x0, y0, n);
               ptx::tma_store_commit();
             }
-            ++slab_ctr;
           }
         }
       } else {
@@ -273,7 +352,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           uint32_t r[16];
           ptx::tmem_ld16(taddr + c0, r);
           ptx::tmem_ld_wait();
-          if (in_img && !(p.flags & DBG_SKIP_STORE)) {
+          if (in_img) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int co = n0 + c0 + 8 * h;
@@ -339,17 +418,18 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int C, int TW, int TH) {
+// (C, W, H, N) view of an NHWC tensor; box = {box_c channels, TW, TH, 1}
+static int encode_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int C, int TW, int TH, int box_c, bool swizzle) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations %dx%dx%dx%d box %dx%d) failed: %d", N, H, W, C, TH, TW, (int)r); return FOSVOS_ERR_DRIVER; }
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations %dx%dx%dx%d box %dx%dx%d) failed: %d", N, H, W, C, TH, TW, box_c, (int)r); return FOSVOS_ERR_DRIVER; }
   return FOSVOS_OK;
 }
 
@@ -379,19 +459,100 @@ static int pick_tw_shift(int H, int W) {
   return best;
 }
 
-template <int BN>
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FOSVOS_PDL"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v == 1;
+}
+
+template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
     attr_set = true;
   }
   int grid = min(p.total_tiles, num_sms());
   if (const char* e = getenv("FOSVOS_TC_GRID")) { const int v = atoi(e); if (v > 0) grid = min(grid, v); }
-  conv3x3_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, my, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, MODE>, mx, mw, my, p);
+  if (e != cudaSuccess) { set_error("conv3x3_tc launch: %s", cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
   return check_launch("conv3x3_tc");
+}
+
+static int conv_tc_common(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, int N, int H,
+                          int W, int Cin, int Cout, int taps, int flags, fosvos_stream_t stream, const char* what) {
+  FOSVOS_REQUIRE(x && w_packed && y && N > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", what);
+  FOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin > 0 && Cout > 0,
+                 "%s: Cin=%d and Cout=%d must be positive multiples of 8 (pad the NHWC tensors)", what, Cin, Cout);
+  FOSVOS_REQUIRE(!(flags & FOSVOS_CONV_BIAS) || bias, "%s: BIAS flag without bias pointer", what);
+  FOSVOS_REQUIRE(!(flags & FOSVOS_CONV_MASK) || mask, "%s: MASK flag without mask pointer", what);
+  FOSVOS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                 "%s: pointers must be 16-byte aligned", what);
+  TcParams p;
+  p.bias = bias;
+  p.mask = (const __nv_bfloat16*)mask;
+  p.y = (__nv_bfloat16*)y;
+  p.w = (const __nv_bfloat16*)w_packed;
+  p.N = N; p.H = H; p.W = W; p.CoutP = Cout;
+  p.tw_shift = pick_tw_shift(H, W);
+  const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
+  p.tiles_x = ceil_div(W, TW);
+  p.tiles_y = ceil_div(H, TH);
+  p.k_chunks = ceil_div(Cin, TC_BK);
+  p.cin_pad = p.k_chunks * TC_BK;
+  p.taps = taps;
+  p.flags = flags;
+  const bool c8 = taps == 9 && Cin == 8 && Cout <= 64 && !getenv("FOSVOS_TC_NO_C8");
+  const long long m_tiles = (long long)N * p.tiles_x * p.tiles_y;
+  // N tile: minimise waves x cycles per tile.  One M=128 tcgen05.mma costs max(N/2, ~57) cycles
+  // (tools/exp/mma_issue.cu), so tiles narrower than 128 only pay when they fill an otherwise idle machine.
+  int BN = 16;
+  {
+    int cap = 16;
+    while (cap < Cout && cap < 256) cap *= 2;
+    double best_cost = -1.0;
+    for (int bn = cap; bn >= 64; bn >>= 1) {
+      const long long waves = ceil_div_ll(m_tiles * ceil_div(Cout, bn), num_sms());
+      const double cost = (double)waves * (bn >= 128 ? bn / 2 : 57);
+      // wider tiles re-read less of the activation and drain fewer accumulators: a narrower one must win clearly
+      if (best_cost < 0 || cost < 0.88 * best_cost) { best_cost = cost; BN = bn; }
+    }
+    if (cap < 64) BN = cap;
+  }
+  if (const char* e = getenv("FOSVOS_TC_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && (v & (v - 1)) == 0) BN = v; }
+  if (c8) BN = 64;
+  p.n_tiles_n = ceil_div(Cout, BN);
+  FOSVOS_REQUIRE(m_tiles * p.n_tiles_n < (1LL << 31), "%s: too many tiles", what);
+  p.total_tiles = (int)(m_tiles * p.n_tiles_n);
+
+  CUtensorMap mx, mw, my;
+  int rc = c8 ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH, 8, false) : encode_act_map(&mx, x, N, H, W, Cin, TW, TH, TC_BK, true);
+  if (rc) return rc;
+  rc = encode_act_map(&my, y, N, H, W, Cout, TW, TH, TC_BK, true);      // output slabs leave through TMA stores (BN >= 64)
+  if (rc) return rc;
+  rc = encode_w_map(&mw, w_packed, Cout, taps * p.cin_pad, BN);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (c8) return launch_tc<64, MODE_C8>(mx, mw, my, p, st);
+  switch (BN) {
+    case 16: return launch_tc<16, MODE_GENERIC>(mx, mw, my, p, st);
+    case 32: return launch_tc<32, MODE_GENERIC>(mx, mw, my, p, st);
+    case 64: return launch_tc<64, MODE_GENERIC>(mx, mw, my, p, st);
+    case 128: return launch_tc<128, MODE_GENERIC>(mx, mw, my, p, st);
+    default: return launch_tc<256, MODE_GENERIC>(mx, mw, my, p, st);
+  }
 }
 
 }  // namespace fosvos
@@ -402,50 +563,7 @@ extern "C" {
 
 int fosvos_conv3x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, int N, int H,
                       int W, int Cin, int Cout, int flags, fosvos_stream_t stream) {
-  FOSVOS_REQUIRE(x && w_packed && y && N > 0 && H > 0 && W > 0, "conv3x3_tc: null pointer or empty shape");
-  FOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin > 0 && Cout > 0,
-                 "conv3x3_tc: Cin=%d and Cout=%d must be positive multiples of 8 (pad the NHWC tensors)", Cin, Cout);
-  FOSVOS_REQUIRE(!(flags & FOSVOS_CONV_BIAS) || bias, "conv3x3_tc: BIAS flag without bias pointer");
-  FOSVOS_REQUIRE(!(flags & FOSVOS_CONV_MASK) || mask, "conv3x3_tc: MASK flag without mask pointer");
-  FOSVOS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0,
-                 "conv3x3_tc: pointers must be 16-byte aligned");
-  TcParams p;
-  p.bias = bias;
-  p.mask = (const __nv_bfloat16*)mask;
-  p.y = (__nv_bfloat16*)y;
-  p.N = N; p.H = H; p.W = W; p.CoutP = Cout;
-  p.tw_shift = pick_tw_shift(H, W);
-  const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
-  p.tiles_x = ceil_div(W, TW);
-  p.tiles_y = ceil_div(H, TH);
-  p.k_chunks = ceil_div(Cin, TC_BK);
-  p.cin_pad = p.k_chunks * TC_BK;
-  p.flags = flags;
-  int BN = 16;
-  while (BN < Cout && BN < 256) BN *= 2;
-  // small grids: prefer narrower N tiles so that more SMs get work
-  const long long m_tiles = (long long)N * p.tiles_x * p.tiles_y;
-  while (BN > 64 && m_tiles * ceil_div(Cout, BN) < num_sms()) BN /= 2;
-  if (const char* e = getenv("FOSVOS_TC_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && (v & (v - 1)) == 0) BN = v; }
-  p.n_tiles_n = ceil_div(Cout, BN);
-  FOSVOS_REQUIRE(m_tiles * p.n_tiles_n < (1LL << 31), "conv3x3_tc: too many tiles");
-  p.total_tiles = (int)(m_tiles * p.n_tiles_n);
-
-  CUtensorMap mx, mw, my;
-  int rc = encode_act_map(&mx, x, N, H, W, Cin, TW, TH);
-  if (rc) return rc;
-  rc = encode_act_map(&my, y, N, H, W, Cout, TW, TH);      // output slabs leave through TMA stores (BN >= 64)
-  if (rc) return rc;
-  rc = encode_w_map(&mw, w_packed, Cout, 9 * p.cin_pad, BN);
-  if (rc) return rc;
-  cudaStream_t st = as_stream(stream);
-  switch (BN) {
-    case 16: return launch_tc<16>(mx, mw, my, p, st);
-    case 32: return launch_tc<32>(mx, mw, my, p, st);
-    case 64: return launch_tc<64>(mx, mw, my, p, st);
-    case 128: return launch_tc<128>(mx, mw, my, p, st);
-    default: return launch_tc<256>(mx, mw, my, p, st);
-  }
+  return conv_tc_common(x, w_packed, bias, mask, y, N, H, W, Cin, Cout, 9, flags, stream, "conv3x3_tc");
 }
 
 }  // extern "C"

@@ -11,6 +11,7 @@ from fosvos_b200 import synth
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+mode = sys.argv[3] if len(sys.argv) > 3 else "both"      # both | ft | inf
 dev = torch.device("cuda:0")
 net = FB.OSVOS_VGG(pretrained=0)
 net.load_state_dict(synth.make_state_dict(0, "structured"))
@@ -21,7 +22,9 @@ xb = torch.cat([torch.roll(x, i, 3) for i in range(batch)]).to(dev)
 x, m = x.to(dev), m.to(dev)
 opt = FB.get_optimizer_online(net)
 for _ in range(reps):
-    net.predict(xb)
-    FB.finetune(net, x, m, 1, 1, optimizer=opt)
+    if mode in ("both", "inf"):
+        net.predict(xb)
+    if mode in ("both", "ft"):
+        FB.finetune(net, x, m, 1, 1, optimizer=opt)
 torch.cuda.synchronize()
 print("profile_step ok")

@@ -14,17 +14,29 @@ LAYERS = [(480, 854, 3, 64), (480, 854, 64, 64), (240, 427, 64, 128), (240, 427,
           (60, 107, 512, 16), (30, 54, 512, 512), (30, 54, 512, 16)]
 
 
-def timeit(fn, reps=10):
+def timeit(fn, reps=20):
+    """GPU time per call: `reps` calls captured in one CUDA graph (no host launch gaps), replayed 3x."""
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e3
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            g.replay()
+            e1.record(st)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / reps * 1e3)
+    return best
 
 
 for (h, w, cin, cout) in LAYERS:
