@@ -36,6 +36,8 @@ SIGNATURES = {
     "fosvos_conv3x3_wgrad_simt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_tc_workspace_bytes": (C.c_size_t, [_i, _i]),
     "fosvos_conv3x3_wgrad_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_conv3x3_wgrad_tc_accumulate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_conv3x3_wgrad_tc_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_maxpool2x2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_params_bytes": (C.c_size_t, []),

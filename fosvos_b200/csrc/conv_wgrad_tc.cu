@@ -15,7 +15,14 @@
 //   X_IS_A = 0:  M = cout (dZ is A), N = cin tile      -> workspace [tap][cout][cin]
 //   X_IS_A = 1:  M = cin  (X  is A), N = cout tile     -> workspace [tap][cin][cout]   (side_prep, N = 16)
 // Split-K partial sums are merged with vectorised fp32 reductions (red.global.add.v4.f32) into a
-// [tap][M][N] workspace; `wgrad_unpack_kernel` then adds it into the OIHW fp32 .grad tensor.
+// [tap][M][N] workspace; `wgrad_unpack_kernel` then adds it into the OIHW fp32 .grad tensor.  The
+// workspace may stay live across micro-iterations (`_accumulate` / `_finish`), so the unpack runs once
+// per optimizer step.
+// Bias gradient db[co] = sum_p dZ[p][co]: the dZ boxes are in shared memory anyway, so in the CTAs that
+// see every (pixel, cout) exactly once (s == 0 and the first tile of the X-channel dimension) the four
+// epilogue warps, otherwise idle until the accumulators are complete, sum them on the side.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -28,6 +35,8 @@ constexpr int WG_PLAIN_BLOCK = 128 * 128;          // bytes of one un-shifted 64
 
 struct WgParams {
   float* ws;                 // [9][Mtot][Ntot] fp32
+  float* db;                 // bias gradient (Cout fp32, accumulated) or null
+  int cout;                  // real output channels (db length)
   int N, H, W;
   int Mtot, Ntot;            // padded channel counts of the M and N dimensions
   int m_tiles, n_tiles, splits;
@@ -64,23 +73,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* done_bar = empty_bar + p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform roles
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&map_x);
-    ptx::prefetch_tensormap(&map_z);
-    for (int i = 0; i < p.stages; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
-    }
-    ptx::mbar_init(done_bar, 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) ptx::tmem_alloc(tmem_ptr, 512);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  __shared__ float bias_red[128];
 
   // work item
   int item = blockIdx.x;
@@ -88,6 +81,26 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const int s = item % 3; item /= 3;
   const int nt = item % p.n_tiles;
   const int mt = item / p.n_tiles;
+  // this CTA also sums dZ over its pixels (see the header comment)
+  const bool do_bias = p.db != nullptr && s == 0 && (p.x_is_a ? mt == 0 : nt == 0);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform roles
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_z);
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], do_bias ? 5 : 1);      // MMA commit (+ the four bias-summing warps)
+    }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 128) bias_red[threadIdx.x] = 0.f;
+  if (warp == 1) ptx::tmem_alloc(tmem_ptr, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
   const int p_begin = (int)((long long)p.patches * split / p.splits);
   const int p_end = (int)((long long)p.patches * (split + 1) / p.splits);
   const int TW = 1 << p.tw_shift, TH = 128 >> p.tw_shift;
@@ -161,6 +174,48 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     // ===================== epilogue: TMEM -> vectorised fp32 reductions =====================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    if (do_bias) {
+      // thread t of the 128: 16-byte chunk c (8 channels) of pixel rows rg, rg + 16, ... of every dZ box.
+      // SWIZZLE_128B puts chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4); r & 7 == rg & 7 for all its rows.
+      const int t = threadIdx.x - 64;
+      const int c = t & 7, rg = t >> 3;
+      const uint32_t off = (uint32_t)rg * 128 + (uint32_t)((c ^ (rg & 7)) << 4);
+      float acc[2][8];
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[b][e] = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = p_begin; pt < p_end; ++pt) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        const uint8_t* zb = smem + stage * p.stage_bytes + z_off + off;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (b < nb_z) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 v = *reinterpret_cast<const uint4*>(zb + b * WG_PLAIN_BLOCK + j * 2048);
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                acc[b][2 * q] += __uint_as_float(w[q] << 16);
+                acc[b][2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&bias_red[b * 64 + c * 8 + e], acc[b][e]);
+      ptx::named_bar_sync(1, 128);
+      if (zc0 + t < p.cout && t < 64 * nb_z) atomicAdd(p.db + zc0 + t, bias_red[t]);
+    }
     if (p_end > p_begin) {
       ptx::mbar_wait(done_bar, 0);
       ptx::tc_fence_after();
@@ -196,8 +251,9 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 }
 
 // dw_oihw[co][ci][tap] += ws[tap][a][b];  ws is [tap][cout][cin] (x_is_a = 0) or [tap][cin][cout]
-__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int CoutP,
-                                    int CinP, int x_is_a) {
+// (padded rows / columns of ws only ever receive zeros, so they need no clearing)
+__global__ void wgrad_unpack_kernel(float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int CoutP,
+                                    int CinP, int x_is_a, int zero_ws) {
   const int total = Cout * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     // fastest index follows the workspace's contiguous dimension -> coalesced reads
@@ -207,33 +263,11 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restr
     const long long src = x_is_a ? ((long long)ci * CoutP + co) : ((long long)co * CinP + ci);
     float* d = dw + ((long long)co * Cin + ci) * 9;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) d[t] += ws[t * plane + src];
+    for (int t = 0; t < 9; ++t) {
+      d[t] += ws[t * plane + src];
+      if (zero_ws) ws[t * plane + src] = 0.f;
+    }
   }
-}
-
-// db[co] += sum over pixels of dz[p][co]
-template <typename T>
-__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dz, float* __restrict__ db, long long pixels, int CoutP, int Cout) {
-  const int groups = CoutP / 8;
-  const int g = threadIdx.x % groups;               // blockDim.x is a multiple of groups (host guarantees)
-  const int lanes = blockDim.x / groups;
-  const int pl = threadIdx.x / groups;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (long long px = (long long)blockIdx.x * lanes + pl; px < pixels; px += (long long)gridDim.x * lanes) {
-    float v[8];
-    load8(dz + px * CoutP + g * 8, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
-  }
-  __shared__ float sm[512];
-  for (int i = threadIdx.x; i < CoutP; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&sm[g * 8 + j], acc[j]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) atomicAdd(db + i, sm[i]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -275,19 +309,23 @@ extern "C" {
 
 size_t fosvos_conv3x3_wgrad_tc_workspace_bytes(int CinP, int CoutP) { return (size_t)9 * CinP * CoutP * sizeof(float); }
 
-int fosvos_conv3x3_wgrad_tc(const void* x, const void* dz, float* dw, float* db, void* workspace, int N, int H, int W,
-                            int CinP, int CoutP, int Cin, int Cout, fosvos_stream_t stream) {
-  FOSVOS_REQUIRE(x && dz && dw && workspace && N > 0 && H > 0 && W > 0, "conv3x3_wgrad_tc: null pointer or empty shape");
-  FOSVOS_REQUIRE(CinP % 8 == 0 && CoutP % 8 == 0 && CinP > 0 && CoutP > 0 && Cin > 0 && Cin <= CinP && Cout > 0 && Cout <= CoutP,
-                 "conv3x3_wgrad_tc: bad channel counts (CinP=%d CoutP=%d Cin=%d Cout=%d)", CinP, CoutP, Cin, Cout);
+// orientation: put the wider channel dimension on M (=128 rows); tiny couts (side_prep) go to N
+static inline int wg_x_is_a(int CinP, int CoutP) { return (CoutP < 64 || (CinP >= 128 && CoutP < 128)) ? 1 : 0; }
+
+int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db, void* workspace, int N, int H, int W,
+                                       int CinP, int CoutP, int Cout, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(x && dz && workspace && N > 0 && H > 0 && W > 0, "conv3x3_wgrad_tc: null pointer or empty shape");
+  FOSVOS_REQUIRE(CinP % 8 == 0 && CoutP % 8 == 0 && CinP > 0 && CoutP > 0 && Cout > 0 && Cout <= CoutP,
+                 "conv3x3_wgrad_tc: bad channel counts (CinP=%d CoutP=%d Cout=%d)", CinP, CoutP, Cout);
   FOSVOS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dz & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
                  "conv3x3_wgrad_tc: pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   WgParams p;
   p.ws = (float*)workspace;
+  p.db = db;
+  p.cout = Cout;
   p.N = N; p.H = H; p.W = W;
-  // orientation: put the wider channel dimension on M (=128 rows); tiny couts (side_prep) go to N
-  p.x_is_a = (CoutP < 64 || (CinP >= 128 && CoutP < 128)) ? 1 : 0;
+  p.x_is_a = wg_x_is_a(CinP, CoutP);
   p.Mtot = p.x_is_a ? CinP : CoutP;
   p.Ntot = p.x_is_a ? CoutP : CinP;
   p.n_cols = p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
@@ -313,8 +351,13 @@ int fosvos_conv3x3_wgrad_tc(const void* x, const void* dz, float* dw, float* db,
   p.stage_bytes = x_bytes + z_bytes;
   p.stages = min(6, (220 * 1024 - 2048) / p.stage_bytes);
   FOSVOS_REQUIRE(p.stages >= 2, "conv3x3_wgrad_tc: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+  // Split-K over pixel ranges.  Every CTA ends with 3 * 128 * n_cols fp32 reductions into the workspace, so the
+  // split count trades tensor-core occupancy against reduction traffic: fill the machine once; go to a second
+  // wave only while each CTA still has enough patches to amortise its epilogue.
   const int items = p.m_tiles * p.n_tiles * 3;
-  int splits = max(1, (2 * num_sms()) / items);
+  int splits = max(1, num_sms() / items);
+  if ((long long)p.patches >= 16LL * 2 * num_sms() / items) splits = max(1, (2 * num_sms()) / items);
+  if (const char* e = getenv("FOSVOS_WG_SPLITS")) { const int v = atoi(e); if (v > 0) splits = v; }
   splits = min(splits, p.patches);
   p.splits = splits;
 
@@ -324,30 +367,33 @@ int fosvos_conv3x3_wgrad_tc(const void* x, const void* dz, float* dw, float* db,
   rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, TH);
   if (rc) return rc;
 
-  cudaMemsetAsync(workspace, 0, fosvos_conv3x3_wgrad_tc_workspace_bytes(CinP, CoutP), st);
   const int smem_bytes = p.stages * p.stage_bytes + 1024 + 1024;
   static int smem_set = 0;
   if (smem_bytes > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad smem): %s", cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
-    smem_set = 227 * 1024;
+    smem_set = 226 * 1024;
   }
   conv3x3_wgrad_tc_kernel<<<items * splits, WG_THREADS, smem_bytes, st>>>(mx, mz, p);
-  rc = check_launch("conv3x3_wgrad_tc");
+  return check_launch("conv3x3_wgrad_tc");
+}
+
+int fosvos_conv3x3_wgrad_tc_finish(void* workspace, float* dw, int CinP, int CoutP, int Cin, int Cout, int zero_workspace,
+                                   fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(workspace && dw && Cin > 0 && Cin <= CinP && Cout > 0 && Cout <= CoutP, "conv3x3_wgrad_tc_finish: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  wgrad_unpack_kernel<<<min(num_sms() * 8, ceil_div(Cout * Cin, 256)), 256, 0, st>>>((float*)workspace, dw, Cout, Cin, CoutP, CinP,
+                                                                                    wg_x_is_a(CinP, CoutP), zero_workspace);
+  return check_launch("wgrad_unpack");
+}
+
+int fosvos_conv3x3_wgrad_tc(const void* x, const void* dz, float* dw, float* db, void* workspace, int N, int H, int W,
+                            int CinP, int CoutP, int Cin, int Cout, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(dw && workspace && Cin > 0 && Cin <= CinP, "conv3x3_wgrad_tc: null pointer or bad Cin");
+  cudaMemsetAsync(workspace, 0, fosvos_conv3x3_wgrad_tc_workspace_bytes(CinP, CoutP), as_stream(stream));
+  int rc = fosvos_conv3x3_wgrad_tc_accumulate(x, dz, db, workspace, N, H, W, CinP, CoutP, Cout, stream);
   if (rc) return rc;
-  wgrad_unpack_kernel<<<min(num_sms() * 8, ceil_div(Cout * Cin, 256)), 256, 0, st>>>(p.ws, dw, Cout, Cin, CoutP, CinP, p.x_is_a);
-  rc = check_launch("wgrad_unpack");
-  if (rc) return rc;
-  if (db) {
-    FOSVOS_REQUIRE(CoutP <= 512, "conv3x3_wgrad_tc: bias gradient supports up to 512 output channels");
-    const int groups = CoutP / 8;
-    const int threads = max(groups, (256 / groups) * groups);
-    const long long pixels = (long long)N * H * W;
-    const int blocks = (int)min((long long)num_sms() * 4, ceil_div_ll(pixels, threads / groups));
-    bias_grad_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)dz, db, pixels, CoutP, Cout);
-    rc = check_launch("bias_grad");
-  }
-  return rc;
+  return fosvos_conv3x3_wgrad_tc_finish(workspace, dw, CinP, CoutP, Cin, Cout, 0, stream);
 }
 
 }  // extern "C"

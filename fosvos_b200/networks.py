@@ -226,8 +226,12 @@ class OSVOS_VGG(nn.Module):
                          params=params)
         return outs, prob, mask, saved
 
-    def _run_backward(self, saved, douts: Sequence[Optional[torch.Tensor]], grads: Dict[str, torch.Tensor]) -> None:
-        """Accumulate (+=) parameter gradients into ``grads`` (name -> fp32 tensor, reference layout)."""
+    def _run_backward(self, saved, douts: Sequence[Optional[torch.Tensor]], grads: Dict[str, torch.Tensor],
+                      wgrad_ws: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """Accumulate (+=) parameter gradients into ``grads`` (name -> fp32 tensor, reference layout).
+        With ``wgrad_ws`` (conv name -> live accumulator, ``ops.wgrad_workspace``) the tensor-core weight
+        gradients are left in their accumulators; the caller folds them into ``grads`` once per optimizer
+        step (``ops.conv3x3_wgrad_finish``)."""
         if self._side_general:
             raise RuntimeError("fosvos_b200: backward through non-diagonal `upscale` weights is not supported "
                                "(the reference keeps them fixed with lr=0, network_provider.py:154-155)")
@@ -238,6 +242,14 @@ class OSVOS_VGG(nn.Module):
             douts = list(douts)
             douts[4] = torch.zeros_like(next(d for d in douts if d is not None))
         g = lambda k: grads.get(k)  # noqa: E731
+
+        def wgrad(name: str, x_in: torch.Tensor, dz: torch.Tensor) -> None:
+            impl_w = self._wgrad_impl(x_in.shape[3])
+            if wgrad_ws is not None and impl_w == "tc":
+                ops.conv3x3_wgrad_accumulate(x_in, dz, wgrad_ws[name], g(name + ".bias"), grads[name + ".weight"].shape[0])
+            else:
+                ops.conv3x3_wgrad(x_in, dz, grads[name + ".weight"], g(name + ".bias"), impl=impl_w)
+
         dsp = ops.side_bwd(sps, saved["params"], douts, H, W, g("fuse.weight"), g("fuse.bias"),
                            [g(f"score_dsn.{i}.weight") for i in range(4)], [g(f"score_dsn.{i}.bias") for i in range(4)])
         convs = self._stage_convs()
@@ -252,8 +264,7 @@ class OSVOS_VGG(nn.Module):
             if si > 0:
                 spc = self.side_prep[si - 1]
                 pc = self._packed_for(spc, need_dgrad=True)
-                ops.conv3x3_wgrad(a_out, dsp[si - 1], grads[f"side_prep.{si - 1}.weight"], g(f"side_prep.{si - 1}.bias"),
-                                  impl=self._wgrad_impl(a_out.shape[3]))
+                wgrad(f"side_prep.{si - 1}", a_out, dsp[si - 1])
                 flags = L.CONV_MASK | (L.CONV_ACCUMULATE if dA is not None else 0)
                 dA = ops.conv3x3(dsp[si - 1], pc.w_dgrad, None, a_out.shape[3], flags, mask=a_out, out=dA, impl=impl)
             dz = dA
@@ -262,7 +273,7 @@ class OSVOS_VGG(nn.Module):
                 k = first[si] + j
                 x_in = saved["conv_in"][k]
                 name = names[si][j]
-                ops.conv3x3_wgrad(x_in, dz, grads[name + ".weight"], g(name + ".bias"), impl=self._wgrad_impl(x_in.shape[3]))
+                wgrad(name, x_in, dz)
                 if si == 0 and j == 0:
                     break
                 pc = self._packed_for(conv, need_dgrad=True)

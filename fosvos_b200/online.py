@@ -101,6 +101,15 @@ class OnlineTrainer:
             if p.grad is None:
                 p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
             self.grads[name] = p.grad
+        # tensor-core weight gradients accumulate in their own [tap][M][N] layout over the micro-iterations and are
+        # folded into .grad once per optimizer step
+        self.wgrad_ws: Optional[Dict[str, torch.Tensor]] = None
+        if self.fused and net._impl() == "tc":
+            self.wgrad_ws = {}
+            for name in self.grads:
+                if name.endswith(".weight") and params[name].dim() == 4 and tuple(params[name].shape[2:]) == (3, 3):
+                    cout, cin = params[name].shape[0], params[name].shape[1]
+                    self.wgrad_ws[name[:-len(".weight")]] = ops.wgrad_workspace(ops.pad8(cin), ops.pad8(cout), dev)
         self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
         self.last_loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.counter = 0
@@ -124,9 +133,16 @@ class OnlineTrainer:
                 total = total + self.deep * li
         self.last_loss.copy_(total)
         self.loss_sum.add_(total)
-        net._run_backward(saved, douts, self.grads)
+        net._run_backward(saved, douts, self.grads, self.wgrad_ws)
+
+    def _fold_wgrads(self) -> None:
+        if self.wgrad_ws:
+            for name, ws in self.wgrad_ws.items():
+                dw = self.grads[name + ".weight"]
+                ops.conv3x3_wgrad_finish(ws, dw, ops.pad8(dw.shape[1]), ops.pad8(dw.shape[0]), zero_workspace=True)
 
     def _step(self) -> None:
+        self._fold_wgrads()
         if self.fused:
             self.optimizer.step_and_zero()
             _repack_in_place(self.net)
@@ -145,6 +161,8 @@ class OnlineTrainer:
             self._calls_micro = L.CALLS[0] - c0
             for g in self.grads.values():
                 g.zero_()
+            for ws in (self.wgrad_ws or {}).values():
+                ws.zero_()
             self.optimizer._ensure_table()          # momentum buffers + device table exist before capture
         torch.cuda.current_stream().wait_stream(s)
         self._micro_graph = torch.cuda.CUDAGraph()
@@ -167,6 +185,8 @@ class OnlineTrainer:
             self.net.load_state_dict(state_dict)
         for g in self.grads.values():
             g.zero_()
+        for ws in (self.wgrad_ws or {}).values():
+            ws.zero_()
         for st in self.optimizer.state.values():
             buf = st.get("momentum_buffer")
             if buf is not None:

@@ -85,6 +85,30 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+def wgrad_workspace(cin_p: int, cout_p: int, device) -> torch.Tensor:
+    """Zeroed [tap][M][N] fp32 accumulator of the tensor-core weight gradient (kept live across micro-iterations)."""
+    return torch.zeros(L.lib().fosvos_conv3x3_wgrad_tc_workspace_bytes(cin_p, cout_p) // 4, dtype=torch.float32, device=device)
+
+
+def conv3x3_wgrad_accumulate(x: torch.Tensor, dz: torch.Tensor, ws: torch.Tensor, db: Optional[torch.Tensor], cout: int) -> None:
+    """ws += gradient of this micro-iteration (tensor cores, bf16 operands); db += sum dz."""
+    L.require_device(x.device)
+    n, h, w, cin_p = x.shape
+    cout_p = dz.shape[3]
+    assert dz.shape[:3] == x.shape[:3] and x.dtype == dz.dtype == torch.bfloat16 and x.is_contiguous() and dz.is_contiguous()
+    assert ws.dtype == torch.float32 and ws.numel() == 9 * cin_p * cout_p
+    L.check(L.lib().fosvos_conv3x3_wgrad_tc_accumulate(x.data_ptr(), dz.data_ptr(), L.ptr(db), ws.data_ptr(), n, h, w, cin_p, cout_p,
+                                                       cout, L.stream()), "conv3x3_wgrad_tc_accumulate")
+
+
+def conv3x3_wgrad_finish(ws: torch.Tensor, dw: torch.Tensor, cin_p: int, cout_p: int, zero_workspace: bool = True) -> None:
+    """dw (OIHW fp32 .grad) += ws ; ws = 0."""
+    L.require_device(ws.device)
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and ws.numel() == 9 * cin_p * cout_p
+    L.check(L.lib().fosvos_conv3x3_wgrad_tc_finish(ws.data_ptr(), dw.data_ptr(), cin_p, cout_p, dw.shape[1], dw.shape[0],
+                                                   int(zero_workspace), L.stream()), "conv3x3_wgrad_tc_finish")
+
+
 def conv3x3_wgrad(x: torch.Tensor, dz: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor], impl: str = "simt") -> None:
     """dw (OIHW fp32) += x (*) dz ; db += sum dz.  Accumulates in place.
     impl 'tc': tcgen05 kernel (bf16 operands); 'simt': direct fp32-FMA kernel."""

@@ -126,6 +126,16 @@ size_t fosvos_conv3x3_wgrad_tc_workspace_bytes(int CinP, int CoutP);
 int fosvos_conv3x3_wgrad_tc(const void* x, const void* dz, float* dw_oihw, float* db, void* workspace,
                             int N, int H, int W, int CinP, int CoutP, int Cin, int Cout,
                             fosvos_stream_t stream);
+/* The same in two steps, for gradient accumulation over micro-iterations (train_online.py:93-101,
+ * `avg_grad_every_n`): `_accumulate` adds this call's gradient to a ZERO-INITIALISED workspace that
+ * the caller keeps live (and adds the bias gradient to db, may be NULL); `_finish` adds the
+ * workspace to the OIHW fp32 .grad tensor once per optimizer step and (zero_workspace != 0)
+ * clears it for the next round. */
+int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db, void* workspace,
+                                       int N, int H, int W, int CinP, int CoutP, int Cout,
+                                       fosvos_stream_t stream);
+int fosvos_conv3x3_wgrad_tc_finish(void* workspace, float* dw_oihw, int CinP, int CoutP, int Cin,
+                                   int Cout, int zero_workspace, fosvos_stream_t stream);
 
 /* ---- 2x2 / stride-2 max pooling, ceil_mode=True (nn.MaxPool2d, osvos_vgg.py:90) ---- */
 int fosvos_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype,

@@ -162,6 +162,35 @@ def test_conv3x3_wgrad_tc(case):
     assert torch.allclose(db.cpu() + 2.0, gb.float(), rtol=1e-4, atol=5e-3)
 
 
+@pytest.mark.parametrize("case", [(1, 16, 24, 8, 64), (1, 19, 40, 64, 64), (2, 9, 30, 128, 16), (1, 30, 54, 512, 512), (1, 12, 20, 40, 72)])
+@pytest.mark.parametrize("splits", [None, 1, 5])
+def test_conv3x3_wgrad_tc_accumulate_finish(case, splits, monkeypatch):
+    """Two micro-iterations accumulate in the live [tap][M][N] workspace (bias gradient summed by the idle
+    epilogue warps of the same kernel), one `finish` folds them into the OIHW .grad and clears the workspace."""
+    n, h, w_, cin, cout = case
+    if splits is not None:
+        monkeypatch.setenv("FOSVOS_WG_SPLITS", str(splits))
+    g = _gen(23)
+    cinp, coutp = ops.pad8(cin), ops.pad8(cout)
+    ws = ops.wgrad_workspace(cinp, coutp, DEV)
+    dw = torch.full((cout, cin, 3, 3), 0.25, device=DEV)
+    db = torch.full((cout,), -2.0, device=DEV)
+    gw_ref = torch.zeros(cout, cin, 3, 3, dtype=torch.float64)
+    gb_ref = torch.zeros(cout, dtype=torch.float64)
+    for it in range(2):
+        x = _bf16r(torch.randn(n, cin, h, w_, generator=g))
+        dz = _bf16r(torch.randn(n, cout, h, w_, generator=g))
+        wref = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+        gw_ref += torch.autograd.grad(F.conv2d(x.double(), wref, padding=1), wref, dz.double())[0]
+        gb_ref += dz.double().sum(dim=(0, 2, 3))
+        ops.conv3x3_wgrad_accumulate(_nhwc(x, torch.bfloat16), _nhwc(dz, torch.bfloat16), ws, db, cout)
+    assert torch.equal(dw.cpu(), torch.full((cout, cin, 3, 3), 0.25))         # untouched until the fold
+    ops.conv3x3_wgrad_finish(ws, dw, cinp, coutp, zero_workspace=True)
+    assert torch.allclose(dw.cpu() - 0.25, gw_ref.float(), rtol=1e-4, atol=5e-3), float((dw.cpu() - 0.25 - gw_ref.float()).abs().max())
+    assert torch.allclose(db.cpu() + 2.0, gb_ref.float(), rtol=1e-4, atol=5e-3), float((db.cpu() + 2.0 - gb_ref.float()).abs().max())
+    assert float(ws.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(1, 64, 480 // 8, 854 // 7), (2, 16, 7, 9), (1, 8, 1, 1), (1, 24, 30, 107)])
 def test_maxpool_fwd_bwd(dt, shape):
@@ -233,6 +262,31 @@ def test_side_chain_forward(dt, general, HW):
         assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=2e-5), float((a.cpu() - b).abs().max())
     p = O.probabilities(outs[4].cpu())
     assert torch.allclose(prob.cpu(), p, atol=1e-6)
+    assert torch.equal(mask.cpu(), O.binarise(prob.cpu()))
+
+
+@pytest.mark.parametrize("HW", [(70, 300), (37, 259), (130, 31)])
+def test_side_chain_fast_path_arbitrary_shared_kernel(HW):
+    """The fast path only needs `upscale` to be diagonal with ONE shared k x k kernel; that kernel (and the
+    `upscale_` one) may be anything, not just the bilinear one.  Sizes cross the 256-column / 32-row strips."""
+    H, W = HW
+    sp, sd = _side_inputs(2, H, W, 21, torch.float32)
+    g = _gen(22)
+    for i in range(4):
+        k = 4 << i
+        shared = torch.randn(k, k, generator=g) * 0.2
+        w = torch.zeros(16, 16, k, k)
+        for c in range(16):
+            w[c, c] = shared
+        sd[f"upscale.{i}.weight"] = w
+        sd[f"upscale_.{i}.weight"] = torch.randn(1, 1, k, k, generator=g) * 0.2
+    ref = _side_ref(sp, sd, H, W)
+    params, dsd = _side_params(sd)
+    assert int(ops.side_check_diagonal([dsd[f"upscale.{i}.weight"] for i in range(4)]).item()) == 0
+    outs, prob, mask = ops.side_fwd([_nhwc(t, torch.float32) for t in sp], params, H, W, general=False, want_prob=True, want_mask=True)
+    for a, b in zip(outs, ref):
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=5e-5), float((a.cpu() - b).abs().max())
+    assert torch.allclose(prob.cpu(), O.probabilities(outs[4].cpu()), atol=1e-6)
     assert torch.equal(mask.cpu(), O.binarise(prob.cpu()))
 
 

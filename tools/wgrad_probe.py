@@ -39,6 +39,7 @@ def timeit(fn, reps=20):
     return best
 
 
+SPLITS = [None] + [int(v) for v in os.environ.get("PROBE_SPLITS", "1,2,3,4,6,8,12").split(",")]
 for (h, w, cin, cout) in LAYERS:
     cinp = ops.pad8(cin)
     x = torch.randn((batch, h, w, cinp), device=dev).to(torch.bfloat16)
@@ -47,18 +48,16 @@ for (h, w, cin, cout) in LAYERS:
     dz = (torch.randn((batch, h, w, cout), device=dev) * 0.1).to(torch.bfloat16)
     flops = 2.0 * batch * h * w * cin * cout * 9
     msg = f"{h}x{w} {cin}->{cout}:"
-    res = {}
-    for impl in ("tc", "simt") if cin == 3 else ("tc",):
-        dw = torch.zeros((cout, cin, 3, 3), device=dev)
-        db = torch.zeros(cout, device=dev)
-        ops.conv3x3_wgrad(x, dz, dw, db, impl=impl)
-        torch.cuda.synchronize()
-        res[impl] = (dw.clone(), db.clone())
-        t = timeit(lambda: ops.conv3x3_wgrad(x, dz, dw, db, impl=impl))
-        t2 = timeit(lambda: ops.conv3x3_wgrad(x, dz, dw, None, impl=impl))
-        msg += f" {impl}={t:.1f}us ({flops / t / 1e6:.0f}TF) nobias={t2:.1f}us"
-    if len(res) == 2:
-        d = (res["tc"][0] - res["simt"][0]).abs().max().item()
-        s = res["simt"][0].abs().max().item()
-        msg += f" | tc-vs-simt max|d|={d:.3e} scale={s:.3e} db d={(res['tc'][1] - res['simt'][1]).abs().max().item():.3e}"
+    ws = ops.wgrad_workspace(cinp, ops.pad8(cout), dev)
+    db = torch.zeros(cout, device=dev)
+    for sp in SPLITS:
+        if sp is None:
+            os.environ.pop("FOSVOS_WG_SPLITS", None)
+        else:
+            os.environ["FOSVOS_WG_SPLITS"] = str(sp)
+        t = timeit(lambda: ops.conv3x3_wgrad_accumulate(x, dz, ws, db, cout))
+        msg += f" {'auto' if sp is None else 's' + str(sp)}={t:.1f}" + (f"us({flops / t / 1e6:.0f}TF)" if sp is None else "")
+    os.environ.pop("FOSVOS_WG_SPLITS", None)
+    t2 = timeit(lambda: ops.conv3x3_wgrad_accumulate(x, dz, ws, None, cout))
+    msg += f" | auto nobias={t2:.1f}"
     print(msg, flush=True)
