@@ -15,8 +15,9 @@
 // Accumulators live in TMEM (2 stages x BN columns) so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Persistent CTAs, one per SM, static round-robin over tiles.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 =
-// two epilogue groups of four warps (group g drains accumulator stage g, i.e. every other tile):
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 =
+// two epilogue groups of eight warps (group g drains accumulator stage g, i.e. every other tile; two warps
+// share a TMEM lane quadrant and split each 64-column slab):
 // TMEM -> registers -> bias/ReLU/mask/accumulate -> bf16 -> swizzled shared-memory slab -> TMA store
 // (which also clips the patch at the frame edge).  The role branches are warp-uniform and the single
 // issuing lane is picked with elect.sync, so descriptors stay in uniform registers (a `lane == 0` branch
@@ -24,10 +25,20 @@
 // The same kernel computes the data gradient (weights packed flipped and transposed, epilogue = ReLU
 // mask [+ accumulate]).
 //
-// MODE_C8 serves the first layer (Cin <= 8, e.g. the 3-channel frame padded to 8): all nine taps of a
-// patch are one pipeline stage of nine {8ch, TW, TH} boxes in the un-swizzled K-major core-matrix
-// layout (tap = one 16-byte K core matrix), the whole 64 x 80 weight stays resident in shared
-// memory, and a tile is five K=16 MMAs instead of 36 mostly-zero ones.
+// MODE_HALO (3x3, the default): the nine shifted 128-pixel boxes of a tile overlap almost completely, and
+// fetching each of them through L2 makes the wide early layers L2->SM bound (9 x 16 KB per 64 channels and
+// tile).  Instead one box {64ch, TW, TH+2} per horizontal shift s is loaded (three per tile and channel slab)
+// and the three vertical taps r read it at r * TW rows, a multiple of the 1024-byte swizzle atom when
+// TW % 8 == 0, so the same SWIZZLE_128B descriptor applies.  Activation boxes and weight tiles travel in two
+// independent mbarrier rings (A: 3-6 halo boxes, B: 4-9 weight tiles), both filled by the producer warp in
+// the order the MMA warp consumes them.
+//
+// MODE_C8 serves the first layer (Cin == 8: the 3-channel frame padded to 8).  A pixel is then 16 bytes = one
+// row of an un-swizzled K-major core matrix, and the frame is described to TMA as (8 W, H, N), so ONE box
+// {(8+2) px x 8 ch, 16+2 rows} per 16 x 8 patch (18 requests of 160 B) holds all nine taps: tap (r, s) is the
+// same tile read from byte offset r * 160 + s * 16, with SBO = 160 (next image row).  A K = 16 step pairs two
+// taps (LBO = their byte distance); the 64 x 80 weight (9 taps + one zero block) stays resident in shared
+// memory and a tile is five MMAs.
 #include <stdlib.h>
 
 #include <mutex>
@@ -39,25 +50,35 @@ namespace fosvos {
 
 constexpr int TC_BM = 128;       // pixels per tile
 constexpr int TC_BK = 64;        // channels per K slab (128 B of bf16 = one swizzle row)
-constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 16;   // two groups of eight
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_BIAS_BYTES = 2048;  // all CoutP <= 512 biases, staged once per CTA
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one 64-channel output slab of a tile
-constexpr int MODE_GENERIC = 0, MODE_C8 = 1;
-constexpr int C8_TAP_BYTES = TC_BM * 16;         // 128 pixels x 8 channels
+constexpr int MODE_GENERIC = 0, MODE_C8 = 1, MODE_HALO = 2;
+constexpr int HALO_A_BYTES = 20 * 1024;          // (TH+2) x TW x 128 B: 18 KB for 16x8 patches, 20 KB for 8x16
+constexpr int C8_ROW_BYTES = (8 + 2) * 16;       // one image row of the halo tile: 10 pixels x 8 channels
+constexpr int C8_BOX_BYTES = (16 + 2) * C8_ROW_BYTES;   // 2880
+constexpr int C8_A_BYTES = 3072;                 // box + zeroed tail (the zero-weight K block reads 16 B past the box)
 constexpr int C8_KBLOCKS = 10;                   // 9 taps + 1 zero-weight pad -> 5 MMAs of K = 16
 constexpr int C8_W_BYTES = C8_KBLOCKS * 64 * 16; // [k block][64 couts][8 ch]
 
 template <int BN, int MODE> struct TcCfg {
-  static constexpr int A_BYTES = MODE == MODE_C8 ? C8_KBLOCKS * C8_TAP_BYTES : TC_A_BYTES;
+  static constexpr int A_BYTES = MODE == MODE_C8 ? C8_A_BYTES : MODE == MODE_HALO ? HALO_A_BYTES : TC_A_BYTES;
   static constexpr int B_BYTES = MODE == MODE_C8 ? 0 : BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = MODE == MODE_C8 ? 6 : (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  // MODE_HALO: two rings -- STAGES halo boxes (A) followed by B_STAGES weight tiles (B); otherwise one ring of A+B
+  static constexpr int STAGE_BYTES = MODE == MODE_HALO ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 3 : (BN >= 128) ? 4 : (BN >= 64) ? 5 : 6)
+                                : MODE == MODE_C8 ? 8 : (BN >= 256) ? 3 : (BN >= 128) ? 5 : (BN >= 64) ? 7 : 8;
+  static constexpr int B_STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 4 : (BN >= 128) ? 6 : 9) : 0;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES + B_STAGES * B_BYTES;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   // BN >= 64: each epilogue group stages 64-channel output slabs (128 px x 128 B, SWIZZLE_128B) for TMA stores
   static constexpr bool STAGED = BN >= 64;
   static constexpr int STAGING_BYTES = STAGED ? 2 * TC_SLAB_BYTES : 0;
   static constexpr int WRES_BYTES = MODE == MODE_C8 ? C8_W_BYTES : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + WRES_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + WRES_BYTES + TC_BIAS_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct TcParams {
@@ -71,6 +92,7 @@ struct TcParams {
   int k_chunks;                  // ceil(CinP / 64)
   int cin_pad;                   // k_chunks * 64: per-tap K extent of the packed weight
   int taps;                      // 9 (3x3, pad 1) or 1 (1x1)
+  int halo_bytes;                // MODE_HALO: (TH+2) * TW * 128
   int flags;
 };
 
@@ -94,13 +116,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint8_t* btiles = smem + Cfg::STAGES * Cfg::STAGE_BYTES;      // MODE_HALO: the weight-tile ring
+  uint8_t* staging = smem + Cfg::RING_BYTES;
   uint8_t* wres = staging + Cfg::STAGING_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wres + Cfg::WRES_BYTES);
+  float* bias_s = reinterpret_cast<float*>(wres + Cfg::WRES_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wres + Cfg::WRES_BYTES + TC_BIAS_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bfull_bar = tmem_empty + 2;
+  uint64_t* bempty_bar = bfull_bar + Cfg::B_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bempty_bar + Cfg::B_STAGES);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -114,7 +140,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 4);     // one arrive per warp of the epilogue group
+      ptx::mbar_init(&tmem_empty[i], TC_EPI_WARPS / 2);     // one arrive per warp of the epilogue group
+    }
+    for (int i = 0; i < Cfg::B_STAGES; ++i) {
+      ptx::mbar_init(&bfull_bar[i], 1);
+      ptx::mbar_init(&bempty_bar[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -123,6 +153,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   // memory is only touched after the wait
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();
+  for (int i = threadIdx.x; i < TC_BIAS_BYTES / 4; i += TC_THREADS)
+    bias_s[i] = ((p.flags & FOSVOS_CONV_BIAS) && i < p.CoutP) ? __ldg(p.bias + i) : 0.f;
   if constexpr (MODE == MODE_C8) {
     // resident weight image [k block][64 couts][8 ch] from the packed [cout][tap][64] layout; block 9 and dead couts = 0
     for (int i = threadIdx.x; i < C8_KBLOCKS * 64; i += TC_THREADS) {
@@ -130,6 +162,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (kb < 9 && co < p.CoutP) v = __ldg(reinterpret_cast<const uint4*>(p.w + ((long long)co * 9 + kb) * 64));
       *reinterpret_cast<uint4*>(wres + i * 16) = v;
+    }
+    // tails of the activation stages: never written by TMA, read (times zero weights) by the last K block
+    for (int i = threadIdx.x; i < Cfg::STAGES * ((C8_A_BYTES - C8_BOX_BYTES) / 16); i += TC_THREADS) {
+      const int st = i / ((C8_A_BYTES - C8_BOX_BYTES) / 16), j = i % ((C8_A_BYTES - C8_BOX_BYTES) / 16);
+      *reinterpret_cast<uint4*>(tiles + st * Cfg::STAGE_BYTES + C8_BOX_BYTES + j * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     ptx::fence_proxy_async_smem();
   }
@@ -147,6 +184,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint32_t phase = 0;
     const uint32_t tiles_a = ptx::smem_u32(tiles), full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
     uint32_t a_dst = tiles_a, bar_full = full_a, bar_empty = empty_a;
+    // weight-tile ring (MODE_HALO)
+    int bstage = 0;
+    uint32_t bphase = 0;
+    const uint32_t btiles_a = ptx::smem_u32(btiles), bfull_a = ptx::smem_u32(bfull_bar), bempty_a = ptx::smem_u32(bempty_bar);
+    uint32_t b_dst = btiles_a, bbar_full = bfull_a, bbar_empty = bempty_a;
+    (void)bstage; (void)bphase; (void)b_dst; (void)bbar_full; (void)bbar_empty;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles_n;
       int m = tile / p.n_tiles_n;
@@ -157,17 +200,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if constexpr (MODE == MODE_C8) {
         ptx::mbar_wait_a(bar_empty, phase ^ 1);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx_a(bar_full, Cfg::A_BYTES);
-#pragma unroll
-          for (int t = 0; t < C8_KBLOCKS; ++t) {
-            const int tap = t < 9 ? t : 8;            // block 9 multiplies zero weights: any finite data will do
-            const int r = tap / 3, s = tap - 3 * r;
-            ptx::tma_load_4d_a(a_dst + t * C8_TAP_BYTES, &map_x, bar_full, 0, x0 + s - 1, y0 + r - 1, n);
-          }
+          ptx::mbar_expect_tx_a(bar_full, C8_BOX_BYTES);
+          ptx::tma_load_3d_a(a_dst, &map_x, bar_full, (x0 - 1) * 8, y0 - 1, n);
         }
         __syncwarp();
         a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_dst = tiles_a; bar_full = full_a; bar_empty = empty_a; }
+      } else if constexpr (MODE == MODE_HALO) {
+        for (int c = 0; c < p.cin_pad; c += TC_BK) {
+          for (int s = 0; s < 3; ++s) {
+            ptx::mbar_wait_a(bar_empty, phase ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx_a(bar_full, p.halo_bytes);
+              ptx::tma_load_4d_a(a_dst, &map_x, bar_full, c, x0 + s - 1, y0 - 1, n);
+            }
+            __syncwarp();
+            a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_dst = tiles_a; bar_full = full_a; bar_empty = empty_a; }
+            for (int r = 0; r < 3; ++r) {
+              ptx::mbar_wait_a(bbar_empty, bphase ^ 1);
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx_a(bbar_full, Cfg::B_BYTES);
+                ptx::tma_load_2d_a(b_dst, &map_w, bbar_full, (3 * r + s) * p.cin_pad + c, n0);
+              }
+              __syncwarp();
+              b_dst += Cfg::B_BYTES; bbar_full += 8; bbar_empty += 8;
+              if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; b_dst = btiles_a; bbar_full = bfull_a; bbar_empty = bempty_a; }
+            }
+          }
+        }
       } else {
         // taps outer, 64-channel chunks inner; no divisions and only running shared-memory addresses in the loop
         const int n_r = p.taps == 9 ? 3 : 1;
@@ -202,6 +263,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t a_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
     const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
     uint32_t a_lo = a_lo0, bar_full = full_a, bar_empty = empty_a;
+    // weight-tile ring (MODE_HALO)
+    int bstage = 0;
+    uint32_t bphase = 0;
+    const uint32_t b_lo0 = (uint32_t)ptx::umma_desc_sw128_kmajor(ptx::smem_u32(btiles));
+    const uint32_t bfull_a = ptx::smem_u32(bfull_bar), bempty_a = ptx::smem_u32(bempty_bar);
+    uint32_t b_lo = b_lo0, bbar_full = bfull_a, bbar_empty = bempty_a;
+    (void)bstage; (void)bphase; (void)b_lo; (void)bbar_full; (void)bbar_empty;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -216,7 +284,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (ptx::elect_one()) {
 #pragma unroll
           for (int j = 0; j < C8_KBLOCKS / 2; ++j) {
-            const uint64_t da = umma_desc_noswizzle_kmajor(a_addr + 2 * j * C8_TAP_BYTES, C8_TAP_BYTES, 128);
+            // K blocks 2j, 2j+1 = taps (r, s) = (2j / 3, 2j % 3) and the next one (block 9: zero weights, one pixel on)
+            const int r0 = (2 * j) / 3, s0 = (2 * j) % 3;
+            const uint32_t lbo = s0 == 2 ? C8_ROW_BYTES - 32 : 16;
+            const uint64_t da = umma_desc_noswizzle_kmajor(a_addr + r0 * C8_ROW_BYTES + s0 * 16, lbo, C8_ROW_BYTES);
             const uint64_t db = umma_desc_noswizzle_kmajor(w_addr + 2 * j * 64 * 16, 64 * 16, 128);
             ptx::umma_bf16(tmem_d, da, db, idesc, j != 0);
           }
@@ -226,6 +297,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         __syncwarp();
         bar_full += 8; bar_empty += 8;
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; bar_full = full_a; bar_empty = empty_a; }
+      } else if constexpr (MODE == MODE_HALO) {
+        const uint32_t tfull = ptx::smem_u32(&tmem_full[as]);
+        const uint32_t tap_step = (uint32_t)(TW * 128) >> 4;      // one image row of the patch, in descriptor units
+        const int n_boxes = 3 * p.k_chunks;
+        uint32_t acc = 0;
+        for (int bx = 0; bx < n_boxes; ++bx) {
+          ptx::mbar_wait_a(bar_full, phase);                // halo box has landed
+          for (int r = 0; r < 3; ++r) {
+            ptx::mbar_wait_a(bbar_full, bphase);            // weight tile of tap (r, s) has landed
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                ptx::umma_bf16_lohi(tmem_d, a_lo + r * tap_step + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc | k);
+              }
+              ptx::umma_commit_a(bbar_empty);
+              if (r == 2) {
+                ptx::umma_commit_a(bar_empty);
+                if (bx == n_boxes - 1) ptx::umma_commit_a(tfull);
+              }
+            }
+            __syncwarp();
+            acc = 1;
+            b_lo += Cfg::B_BYTES >> 4; bbar_full += 8; bbar_empty += 8;
+            if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; b_lo = b_lo0; bbar_full = bfull_a; bbar_empty = bempty_a; }
+          }
+          a_lo += Cfg::STAGE_BYTES >> 4; bar_full += 8; bar_empty += 8;
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; bar_full = full_a; bar_empty = empty_a; }
+        }
       } else {
         const uint32_t tfull = ptx::smem_u32(&tmem_full[as]);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -247,15 +347,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue: group g = warps 2+4g .. 5+4g drains accumulator stage g =====================
-    const int grp = (warp - 2) >> 2;
+    // ===================== epilogue: group g = warps 2+8g .. 9+8g drains accumulator stage g =====================
+    // Two warps share each TMEM lane quadrant of a group and split every 64-column slab in halves: the drain is
+    // a long dependent instruction stream per warp, so its throughput scales with the number of warps.
+    const int e = warp - 2;
+    const int grp = e >> 3;
+    const int half = (e >> 2) & 1;                        // which 32 columns of a slab
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;                     // accumulator row = pixel inside the patch
     const int py = row >> p.tw_shift, px = row & (TW - 1);
-    const bool issuer = (warp == 2 + 4 * grp) && (lane == 0);   // owns this group's TMA-store bulk groups
+    const bool issuer = ((e & 7) == 0) && (lane == 0);    // owns this group's TMA-store bulk groups
     const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+    constexpr int GRP_THREADS = 32 * TC_EPI_WARPS / 2;
     uint8_t* buf = staging + grp * TC_SLAB_BYTES;
     const int as = grp;
+    const bool relu = (p.flags & FOSVOS_CONV_RELU) != 0;
+    const bool post = (p.flags & (FOSVOS_CONV_MASK | FOSVOS_CONV_ACCUMULATE)) != 0;
     int it = grp;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int nt = tile % p.n_tiles_n;
@@ -279,30 +386,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int j = 0; j < SLABS; ++j) {
           const int co0 = n0 + 64 * j;
           const bool live = co0 < p.CoutP;                // uniform: N-tail tiles have dead slabs
-          uint32_t packed[32];
+          uint32_t packed[16];
           if (live) {
-            uint32_t r[64];
-            ptx::tmem_ld32(taddr + 64 * j, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-            ptx::tmem_ld32(taddr + 64 * j + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            uint32_t r[32];
+            ptx::tmem_ld32(taddr + 64 * j + 32 * half, r);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int h = 0; h < 8; ++h) {
-              const int co = co0 + 8 * h;
+            for (int h = 0; h < 4; ++h) {
+              const int co = co0 + 32 * half + 8 * h;    // < 512: bias_s holds zeros past CoutP
               float v[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[8 * h + q]);
-              if (co < p.CoutP) {
-                if (p.flags & FOSVOS_CONV_BIAS) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (p.flags & FOSVOS_CONV_RELU) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + co + 4);
+              v[0] = __uint_as_float(r[8 * h]) + b0.x; v[1] = __uint_as_float(r[8 * h + 1]) + b0.y;
+              v[2] = __uint_as_float(r[8 * h + 2]) + b0.z; v[3] = __uint_as_float(r[8 * h + 3]) + b0.w;
+              v[4] = __uint_as_float(r[8 * h + 4]) + b1.x; v[5] = __uint_as_float(r[8 * h + 5]) + b1.y;
+              v[6] = __uint_as_float(r[8 * h + 6]) + b1.z; v[7] = __uint_as_float(r[8 * h + 7]) + b1.w;
+              if (post) {
+                if (relu) {
 #pragma unroll
                   for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
                 }
-                if ((p.flags & (FOSVOS_CONV_MASK | FOSVOS_CONV_ACCUMULATE)) && in_img) {
+                if (in_img && co < p.CoutP) {
                   const long long o = pix * p.CoutP + co;
                   if (p.flags & FOSVOS_CONV_MASK) {
                     float mk[8];
@@ -317,11 +421,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     for (int q = 0; q < 8; ++q) v[q] += old[q];
                   }
                 }
-              }
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-                packed[4 * h + q] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int q = 0; q < 4; ++q) packed[4 * h + q] = ptx::cvt_bf16x2(v[2 * q], v[2 * q + 1]);
+              } else if (relu) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) packed[4 * h + q] = ptx::cvt_bf16x2_relu(v[2 * q], v[2 * q + 1]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) packed[4 * h + q] = ptx::cvt_bf16x2(v[2 * q], v[2 * q + 1]);
               }
             }
           }
@@ -332,14 +439,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
           if (live) {
             if (issuer) ptx::tma_store_wait_read<0>();    // the previous store of this group has read the buffer
-            ptx::named_bar_sync(bar_a, 128);
+            ptx::named_bar_sync(bar_a, GRP_THREADS);
             uint8_t* rowp = buf + row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) =
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(rowp + (((4 * half + c) ^ (row & 7)) << 4)) =
                   make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
             ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(bar_b, 128);
+            ptx::named_bar_sync(bar_b, GRP_THREADS);
             if (issuer) {
               ptx::tma_store_4d(&map_y, buf, co0, x0, y0, n);
               ptx::tma_store_commit();
@@ -347,37 +454,38 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
         }
       } else {
+        if (half == 0) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t r[16];
-          ptx::tmem_ld16(taddr + c0, r);
-          ptx::tmem_ld_wait();
-          if (in_img) {
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld16(taddr + c0, r);
+            ptx::tmem_ld_wait();
+            if (in_img) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int co = n0 + c0 + 8 * h;
-              if (co < p.CoutP) {
-                float v[8];
+              for (int h = 0; h < 2; ++h) {
+                const int co = n0 + c0 + 8 * h;
+                if (co < p.CoutP) {
+                  float v[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  v[q] = __uint_as_float(r[8 * h + q]);
-                  if (p.flags & FOSVOS_CONV_BIAS) v[q] += __ldg(p.bias + co + q);
-                  if (p.flags & FOSVOS_CONV_RELU) v[q] = fmaxf(v[q], 0.f);
+                  for (int q = 0; q < 8; ++q) {
+                    v[q] = __uint_as_float(r[8 * h + q]) + bias_s[co + q];
+                    if (relu) v[q] = fmaxf(v[q], 0.f);
+                  }
+                  const long long o = pix * p.CoutP + co;
+                  if (p.flags & FOSVOS_CONV_MASK) {
+                    float mk[8];
+                    load8(p.mask + o, mk);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = mk[q] > 0.f ? v[q] : 0.f;
+                  }
+                  if (p.flags & FOSVOS_CONV_ACCUMULATE) {
+                    float old[8];
+                    load8(p.y + o, old);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += old[q];
+                  }
+                  store8(p.y + o, v);
                 }
-                const long long o = pix * p.CoutP + co;
-                if (p.flags & FOSVOS_CONV_MASK) {
-                  float mk[8];
-                  load8(p.mask + o, mk);
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) v[q] = mk[q] > 0.f ? v[q] : 0.f;
-                }
-                if (p.flags & FOSVOS_CONV_ACCUMULATE) {
-                  float old[8];
-                  load8(p.y + o, old);
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) v[q] += old[q];
-                }
-                store8(p.y + o, v);
               }
             }
           }
@@ -433,6 +541,21 @@ static int encode_act_map(CUtensorMap* m, const void* x, int N, int H, int W, in
   return FOSVOS_OK;
 }
 
+// first layer: the (N,H,W,8) frame as (8 W, H, N); box = one 16 x 8 patch with its halo, 10 pixels x 18 rows
+static int encode_c8_map(CUtensorMap* m, const void* x, int N, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
+  cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[3] = {80, 18, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(first layer %dx%dx%d) failed: %d", N, H, W, (int)r); return FOSVOS_ERR_DRIVER; }
+  return FOSVOS_OK;
+}
+
 static int encode_w_map(CUtensorMap* m, const void* w, int rows, int kdim, int BN) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
@@ -448,10 +571,10 @@ static int encode_w_map(CUtensorMap* m, const void* w, int rows, int kdim, int B
 }
 
 // pick the 128-pixel patch shape that wastes the fewest out-of-frame pixels
-static int pick_tw_shift(int H, int W) {
+static int pick_tw_shift(int H, int W, int sh_min, int sh_max) {
   int best = 4;
   long long best_area = -1;
-  for (int sh = 2; sh <= 6; ++sh) {            // TW = 4..64, TH = 32..2
+  for (int sh = sh_min; sh <= sh_max; ++sh) {  // TW = 4..64, TH = 32..2
     const int TW = 1 << sh, TH = TC_BM >> sh;
     const long long area = (long long)ceil_div(H, TH) * TH * ceil_div(W, TW) * TW;
     if (best_area < 0 || area < best_area || (area == best_area && sh == 4)) { best_area = area; best = sh; }
@@ -506,15 +629,18 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   p.y = (__nv_bfloat16*)y;
   p.w = (const __nv_bfloat16*)w_packed;
   p.N = N; p.H = H; p.W = W; p.CoutP = Cout;
-  p.tw_shift = pick_tw_shift(H, W);
+  const bool c8 = taps == 9 && Cin == 8 && Cout <= 64 && !getenv("FOSVOS_TC_NO_C8");
+  // narrow outputs (side_prep, N = 16) are bound by the MMA issue rate, not by L2 traffic: they keep one ring
+  const bool halo = taps == 9 && !c8 && Cout > 32 && !getenv("FOSVOS_TC_NO_HALO");
+  p.tw_shift = c8 ? 3 : halo ? pick_tw_shift(H, W, 3, 4) : pick_tw_shift(H, W, 2, 6);
   const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
+  p.halo_bytes = (TH + 2) * TW * 128;
   p.tiles_x = ceil_div(W, TW);
   p.tiles_y = ceil_div(H, TH);
   p.k_chunks = ceil_div(Cin, TC_BK);
   p.cin_pad = p.k_chunks * TC_BK;
   p.taps = taps;
   p.flags = flags;
-  const bool c8 = taps == 9 && Cin == 8 && Cout <= 64 && !getenv("FOSVOS_TC_NO_C8");
   const long long m_tiles = (long long)N * p.tiles_x * p.tiles_y;
   // N tile: minimise waves x cycles per tile.  One M=128 tcgen05.mma costs max(N/2, ~57) cycles
   // (tools/exp/mma_issue.cu), so tiles narrower than 128 only pay when they fill an otherwise idle machine.
@@ -527,7 +653,7 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
       const long long waves = ceil_div_ll(m_tiles * ceil_div(Cout, bn), num_sms());
       const double cost = (double)waves * (bn >= 128 ? bn / 2 : 57);
       // wider tiles re-read less of the activation and drain fewer accumulators: a narrower one must win clearly
-      if (best_cost < 0 || cost < 0.88 * best_cost) { best_cost = cost; BN = bn; }
+      if (best_cost < 0 || cost < 0.92 * best_cost) { best_cost = cost; BN = bn; }
     }
     if (cap < 64) BN = cap;
   }
@@ -538,7 +664,9 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   p.total_tiles = (int)(m_tiles * p.n_tiles_n);
 
   CUtensorMap mx, mw, my;
-  int rc = c8 ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH, 8, false) : encode_act_map(&mx, x, N, H, W, Cin, TW, TH, TC_BK, true);
+  int rc = c8     ? encode_c8_map(&mx, x, N, H, W)
+           : halo ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH + 2, TC_BK, true)
+                  : encode_act_map(&mx, x, N, H, W, Cin, TW, TH, TC_BK, true);
   if (rc) return rc;
   rc = encode_act_map(&my, y, N, H, W, Cout, TW, TH, TC_BK, true);      // output slabs leave through TMA stores (BN >= 64)
   if (rc) return rc;
@@ -546,6 +674,15 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (c8) return launch_tc<64, MODE_C8>(mx, mw, my, p, st);
+  if (halo) {
+    switch (BN) {
+      case 16: return launch_tc<16, MODE_HALO>(mx, mw, my, p, st);
+      case 32: return launch_tc<32, MODE_HALO>(mx, mw, my, p, st);
+      case 64: return launch_tc<64, MODE_HALO>(mx, mw, my, p, st);
+      case 128: return launch_tc<128, MODE_HALO>(mx, mw, my, p, st);
+      default: return launch_tc<256, MODE_HALO>(mx, mw, my, p, st);
+    }
+  }
   switch (BN) {
     case 16: return launch_tc<16, MODE_GENERIC>(mx, mw, my, p, st);
     case 32: return launch_tc<32, MODE_GENERIC>(mx, mw, my, p, st);
