@@ -38,6 +38,11 @@ SIGNATURES = {
     "fosvos_conv3x3_wgrad_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_tc_accumulate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_tc_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_conv3x3_wgrad_tc_orientation": (_i, [_i, _i]),
+    "fosvos_fold_tile_count": (_i, [_i, _i]),
+    "fosvos_repack_tile_count": (_i, [_i, _i]),
+    "fosvos_wgrad_fold_all": (_i, [_vp, _i, _vp, _i, _vp]),
+    "fosvos_repack_all": (_i, [_vp, _i, _vp, _i, _vp]),
     "fosvos_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_maxpool2x2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_params_bytes": (C.c_size_t, []),

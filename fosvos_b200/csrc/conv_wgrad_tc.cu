@@ -312,6 +312,8 @@ size_t fosvos_conv3x3_wgrad_tc_workspace_bytes(int CinP, int CoutP) { return (si
 // orientation: put the wider channel dimension on M (=128 rows); tiny couts (side_prep) go to N
 static inline int wg_x_is_a(int CinP, int CoutP) { return (CoutP < 64 || (CinP >= 128 && CoutP < 128)) ? 1 : 0; }
 
+int fosvos_conv3x3_wgrad_tc_orientation(int CinP, int CoutP) { return wg_x_is_a(CinP, CoutP); }
+
 int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db, void* workspace, int N, int H, int W,
                                        int CinP, int CoutP, int Cout, fosvos_stream_t stream) {
   FOSVOS_REQUIRE(x && dz && workspace && N > 0 && H > 0 && W > 0, "conv3x3_wgrad_tc: null pointer or empty shape");

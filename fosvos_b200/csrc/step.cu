@@ -1,0 +1,122 @@
+// Optimizer-step companions of the tensor-core path, one launch each for ALL conv layers:
+//   wgrad_fold_kernel : .grad (OIHW fp32) += live [tap][M][N] weight-gradient accumulators; accumulators = 0
+//   repack_kernel     : refresh the packed bf16 weight copies (forward [co][tap][ci64] and data-gradient
+//                       [ci][8-tap][co64] layouts) and the padded fp32 bias from the updated fp32 parameters
+// (reference: optimizer.step() / zero_grad() at train_online.py:99-100; the packed copies are derived data).
+// Both are HBM-bound tile transposes through shared memory: every global access is a contiguous run.
+#include "common.cuh"
+
+namespace fosvos {
+
+constexpr int FOLD_CO = 8, FOLD_CI = 32;            // tile: 8 couts x 32 cins x 9 taps
+constexpr int PACK_CO = 32, PACK_CI = 32;           // tile: 32 couts x 32 cins x 9 taps
+
+// tile t of the flat list belongs to entry e with prefix[e] <= t < prefix[e + 1]
+__device__ __forceinline__ int find_entry(const int* __restrict__ prefix, int n, int t) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(prefix + mid) <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_fold_kernel(const fosvos_fold_entry* __restrict__ table, int n_entries, const int* __restrict__ prefix, int n_tiles) {
+  __shared__ float sm[FOLD_CO * FOLD_CI * 9];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int ei = find_entry(prefix, n_entries, tile);
+    const fosvos_fold_entry e = table[ei];
+    const int local = tile - __ldg(prefix + ei);
+    const int ci_tiles = (e.Cin + FOLD_CI - 1) / FOLD_CI;
+    const int co0 = (local / ci_tiles) * FOLD_CO, ci0 = (local % ci_tiles) * FOLD_CI;
+    const int nco = min(FOLD_CO, e.Cout - co0), nci = min(FOLD_CI, e.Cin - ci0);
+    const long long plane = (long long)e.CoutP * e.CinP;
+    // gather: fastest index follows the workspace's contiguous dimension
+    for (int i = threadIdx.x; i < 9 * FOLD_CO * FOLD_CI; i += 256) {
+      int tap, co_l, ci_l;
+      if (e.x_is_a) { co_l = i % FOLD_CO; ci_l = (i / FOLD_CO) % FOLD_CI; tap = i / (FOLD_CO * FOLD_CI); }
+      else          { ci_l = i % FOLD_CI; co_l = (i / FOLD_CI) % FOLD_CO; tap = i / (FOLD_CO * FOLD_CI); }
+      if (co_l < nco && ci_l < nci) {
+        const int co = co0 + co_l, ci = ci0 + ci_l;
+        float* src = e.ws + tap * plane + (e.x_is_a ? ((long long)ci * e.CoutP + co) : ((long long)co * e.CinP + ci));
+        sm[(co_l * FOLD_CI + ci_l) * 9 + tap] = *src;
+        *src = 0.f;
+      }
+    }
+    __syncthreads();
+    // scatter: per cout a contiguous run of nci * 9 floats of the OIHW gradient
+    const int run = nci * 9;
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+      const int co_l = i / run, r = i - co_l * run;
+      e.dw[((long long)(co0 + co_l) * e.Cin + ci0) * 9 + r] += sm[co_l * FOLD_CI * 9 + r];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+repack_kernel(const fosvos_repack_entry* __restrict__ table, int n_entries, const int* __restrict__ prefix, int n_tiles) {
+  constexpr int PITCH = PACK_CI * 9 + 1;            // odd pitch: conflict-free column reads
+  __shared__ float sm[PACK_CO * PITCH];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int ei = find_entry(prefix, n_entries, tile);
+    const fosvos_repack_entry e = table[ei];
+    const int local = tile - __ldg(prefix + ei);
+    const int ci_tiles = (e.Cin + PACK_CI - 1) / PACK_CI;
+    const int co0 = (local / ci_tiles) * PACK_CO, ci0 = (local % ci_tiles) * PACK_CI;
+    const int nco = min(PACK_CO, e.Cout - co0), nci = min(PACK_CI, e.Cin - ci0);
+    const int run = nci * 9;
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+      const int co_l = i / run, r = i - co_l * run;
+      sm[co_l * PITCH + r] = e.w[((long long)(co0 + co_l) * e.Cin + ci0) * 9 + r];
+    }
+    if (ci0 == 0 && e.bias_out && threadIdx.x < nco)
+      e.bias_out[co0 + threadIdx.x] = e.bias ? e.bias[co0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    __nv_bfloat16* fwd = reinterpret_cast<__nv_bfloat16*>(e.out_fwd);
+    __nv_bfloat16* dgr = reinterpret_cast<__nv_bfloat16*>(e.out_dgrad);
+    if (fwd) {
+      // [co][tap][pad_ci]: ci fastest
+      for (int i = threadIdx.x; i < nco * 9 * PACK_CI; i += 256) {
+        const int ci_l = i % PACK_CI, tap = (i / PACK_CI) % 9, co_l = i / (PACK_CI * 9);
+        if (ci_l < nci)
+          fwd[((long long)(co0 + co_l) * 9 + tap) * e.pad_ci + ci0 + ci_l] = __float2bfloat16_rn(sm[co_l * PITCH + ci_l * 9 + tap]);
+      }
+    }
+    if (dgr) {
+      // [ci][8 - tap][pad_co]: co fastest
+      for (int i = threadIdx.x; i < nci * 9 * PACK_CO; i += 256) {
+        const int co_l = i % PACK_CO, tap = (i / PACK_CO) % 9, ci_l = i / (PACK_CO * 9);
+        if (co_l < nco)
+          dgr[((long long)(ci0 + ci_l) * 9 + (8 - tap)) * e.pad_co + co0 + co_l] = __float2bfloat16_rn(sm[co_l * PITCH + ci_l * 9 + tap]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace fosvos
+
+using namespace fosvos;
+
+extern "C" {
+
+int fosvos_fold_tile_count(int Cout, int Cin) { return ceil_div(Cout, FOLD_CO) * ceil_div(Cin, FOLD_CI); }
+int fosvos_repack_tile_count(int Cout, int Cin) { return ceil_div(Cout, PACK_CO) * ceil_div(Cin, PACK_CI); }
+
+int fosvos_wgrad_fold_all(const fosvos_fold_entry* table, int n_entries, const int* tile_prefix, int n_tiles,
+                          fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(table && tile_prefix && n_entries > 0 && n_tiles > 0, "wgrad_fold_all: bad arguments");
+  wgrad_fold_kernel<<<min(n_tiles, num_sms() * 8), 256, 0, as_stream(stream)>>>(table, n_entries, tile_prefix, n_tiles);
+  return check_launch("wgrad_fold_all");
+}
+
+int fosvos_repack_all(const fosvos_repack_entry* table, int n_entries, const int* tile_prefix, int n_tiles,
+                      fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(table && tile_prefix && n_entries > 0 && n_tiles > 0, "repack_all: bad arguments");
+  repack_kernel<<<min(n_tiles, num_sms() * 6), 256, 0, as_stream(stream)>>>(table, n_entries, tile_prefix, n_tiles);
+  return check_launch("repack_all");
+}
+
+}  // extern "C"

@@ -26,20 +26,37 @@ from .optim import FusedSGD, get_optimizer_online
 
 def _repack_in_place(net: OSVOS_VGG) -> None:
     """Refresh the packed weight copies INTO their existing buffers (their addresses are baked into
-    captured graphs) after the parameters changed."""
+    captured graphs) after the parameters changed.  Tensor-core mode: one launch for all layers."""
     dt = _act_dtype(net.precision)
     tc = net._impl() == "tc"
     convs = [c for st in net._stage_convs() for c in st] + list(net.side_prep)
-    for conv in convs:
-        pc = net._packed.get(id(conv))
-        if pc is None:
-            continue
-        b = conv.bias
-        if pc.w_fwd is not None:
-            ops.pack_weight(conv.weight, L.W_TC_FWD if tc else L.W_SIMT_FWD, dt, out=pc.w_fwd)
-            ops.pad_bias(b, conv.out_channels, conv.weight.device, out=pc.bias)
-        if pc.w_dgrad is not None:
-            ops.pack_weight(conv.weight, L.W_TC_DGRAD if tc else L.W_SIMT_DGRAD, dt, out=pc.w_dgrad)
+    if tc:
+        ent = []
+        for conv in convs:
+            pc = net._packed.get(id(conv))
+            if pc is None or pc.w_fwd is None:
+                continue
+            b = None if conv.bias is None else conv.bias.detach()
+            ent.append((conv.weight.detach(), b, pc.w_fwd, pc.w_dgrad, pc.bias))
+        if ent:
+            key = tuple((w.data_ptr(), 0 if b is None else b.data_ptr(), f.data_ptr(), 0 if d is None else d.data_ptr(), bo.data_ptr())
+                        for w, b, f, d, bo in ent)
+            cached = net.__dict__.get("_repack_table")
+            if cached is None or cached[0] != key:
+                cached = (key, ops.repack_table(ent, ent[0][0].device))
+                net.__dict__["_repack_table"] = cached
+            ops.repack_all(cached[1])
+    else:
+        for conv in convs:
+            pc = net._packed.get(id(conv))
+            if pc is None:
+                continue
+            b = conv.bias
+            if pc.w_fwd is not None:
+                ops.pack_weight(conv.weight, L.W_SIMT_FWD, dt, out=pc.w_fwd)
+                ops.pad_bias(b, conv.out_channels, conv.weight.device, out=pc.bias)
+            if pc.w_dgrad is not None:
+                ops.pack_weight(conv.weight, L.W_SIMT_DGRAD, dt, out=pc.w_dgrad)
     if net._side_params is not None:
         ops.side_params_prepare([m.weight for m in net.upscale], [m.weight for m in net.upscale_],
                                 [m.weight for m in net.score_dsn], [m.bias for m in net.score_dsn],
@@ -110,6 +127,7 @@ class OnlineTrainer:
                 if name.endswith(".weight") and params[name].dim() == 4 and tuple(params[name].shape[2:]) == (3, 3):
                     cout, cin = params[name].shape[0], params[name].shape[1]
                     self.wgrad_ws[name[:-len(".weight")]] = ops.wgrad_workspace(ops.pad8(cin), ops.pad8(cout), dev)
+        self._fold_table = None
         self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
         self.last_loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.counter = 0
@@ -137,9 +155,10 @@ class OnlineTrainer:
 
     def _fold_wgrads(self) -> None:
         if self.wgrad_ws:
-            for name, ws in self.wgrad_ws.items():
-                dw = self.grads[name + ".weight"]
-                ops.conv3x3_wgrad_finish(ws, dw, ops.pad8(dw.shape[1]), ops.pad8(dw.shape[0]), zero_workspace=True)
+            if self._fold_table is None:
+                self._fold_table = ops.fold_table([(ws, self.grads[name + ".weight"]) for name, ws in self.wgrad_ws.items()],
+                                                  self.frame.device)
+            ops.wgrad_fold_all(self._fold_table)
 
     def _step(self) -> None:
         self._fold_wgrads()
@@ -164,6 +183,10 @@ class OnlineTrainer:
             for ws in (self.wgrad_ws or {}).values():
                 ws.zero_()
             self.optimizer._ensure_table()          # momentum buffers + device table exist before capture
+            if self.wgrad_ws and self._fold_table is None:
+                self._fold_table = ops.fold_table([(ws, self.grads[name + ".weight"]) for name, ws in self.wgrad_ws.items()],
+                                                  self.frame.device)
+            _repack_in_place(self.net)              # builds the multi-tensor repack table (host -> device copies)
         torch.cuda.current_stream().wait_stream(s)
         self._micro_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._micro_graph):

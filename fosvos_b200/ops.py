@@ -239,6 +239,61 @@ def bal_loss_bwd(output: torch.Tensor, label: torch.Tensor, size_average: bool, 
     return dx
 
 
+# ---- optimizer-step companions (one launch for all layers) -------------------------------------
+FOLD_ENTRY = np.dtype([("ws", np.uint64), ("dw", np.uint64), ("Cout", np.int32), ("Cin", np.int32), ("CoutP", np.int32),
+                       ("CinP", np.int32), ("x_is_a", np.int32), ("pad_", np.int32)])
+REPACK_ENTRY = np.dtype([("w", np.uint64), ("bias", np.uint64), ("out_fwd", np.uint64), ("out_dgrad", np.uint64),
+                         ("bias_out", np.uint64), ("Cout", np.int32), ("Cin", np.int32), ("pad_ci", np.int32), ("pad_co", np.int32)])
+
+
+def _tile_table(tab: np.ndarray, counts: Sequence[int], device):
+    prefix = np.zeros(len(counts) + 1, dtype=np.int32)
+    prefix[1:] = np.cumsum(np.asarray(counts, dtype=np.int64))
+    return (torch.from_numpy(tab.view(np.uint8).copy()).to(device), torch.from_numpy(prefix).to(device), len(counts), int(prefix[-1]))
+
+
+def fold_table(entries: Sequence[Tuple[torch.Tensor, torch.Tensor]], device):
+    """entries: (accumulator ws, OIHW fp32 gradient dw) per conv -> device table for `wgrad_fold_all`."""
+    assert FOLD_ENTRY.itemsize == 40
+    tab = np.zeros(len(entries), dtype=FOLD_ENTRY)
+    counts = []
+    for i, (ws, dw) in enumerate(entries):
+        cout, cin = int(dw.shape[0]), int(dw.shape[1])
+        coutp, cinp = pad8(cout), pad8(cin)
+        assert ws.dtype == dw.dtype == torch.float32 and dw.is_contiguous() and ws.numel() == 9 * coutp * cinp
+        tab[i] = (ws.data_ptr(), dw.data_ptr(), cout, cin, coutp, cinp, L.lib().fosvos_conv3x3_wgrad_tc_orientation(cinp, coutp), 0)
+        counts.append(L.lib().fosvos_fold_tile_count(cout, cin))
+    return _tile_table(tab, counts, device)
+
+
+def wgrad_fold_all(table) -> None:
+    t, prefix, n, tiles = table
+    L.check(L.lib().fosvos_wgrad_fold_all(t.data_ptr(), n, prefix.data_ptr(), tiles, L.stream()), "wgrad_fold_all")
+
+
+def repack_table(entries, device):
+    """entries: (weight OIHW fp32, bias or None, packed fwd or None, packed dgrad or None, padded bias or None)."""
+    assert REPACK_ENTRY.itemsize == 56
+    tab = np.zeros(len(entries), dtype=REPACK_ENTRY)
+    counts = []
+    for i, (w, b, fwd, dgr, bo) in enumerate(entries):
+        cout, cin = int(w.shape[0]), int(w.shape[1])
+        coutp, cinp = pad8(cout), pad8(cin)
+        pad_ci, pad_co = (cinp + 63) // 64 * 64, (coutp + 63) // 64 * 64
+        assert w.dtype == torch.float32 and w.is_contiguous()
+        assert fwd is None or (fwd.dtype == torch.bfloat16 and fwd.numel() == 9 * coutp * pad_ci)
+        assert dgr is None or (dgr.dtype == torch.bfloat16 and dgr.numel() == 9 * cinp * pad_co)
+        tab[i] = (w.data_ptr(), 0 if b is None else b.data_ptr(), 0 if fwd is None else fwd.data_ptr(),
+                  0 if dgr is None else dgr.data_ptr(), 0 if bo is None else bo.data_ptr(), cout, cin, pad_ci, pad_co)
+        counts.append(L.lib().fosvos_repack_tile_count(cout, cin))
+    return _tile_table(tab, counts, device)
+
+
+def repack_all(table) -> None:
+    t, prefix, n, tiles = table
+    L.check(L.lib().fosvos_repack_all(t.data_ptr(), n, prefix.data_ptr(), tiles, L.stream()), "repack_all")
+
+
 # ---- optimizer ------------------------------------------------------------------------------
 SGD_ENTRY = np.dtype([("p", np.uint64), ("g", np.uint64), ("buf", np.uint64), ("n", np.int64), ("lr", np.float32),
                       ("wd", np.float32)])

@@ -218,6 +218,36 @@ int fosvos_sgd_chunk_elems(void); /* elements per work item: chunk_prefix[t] = s
 int fosvos_sgd_step(const fosvos_sgd_entry* table, int n_tensors, const long long* chunk_prefix,
                     int n_chunks, float momentum, int zero_grad, fosvos_stream_t stream);
 
+/* ---- optimizer-step companions of the tensor-core path: ONE launch each for all conv layers ----
+ * fold: for every entry  dw (OIHW fp32 .grad) += ws ([tap][M][N] accumulator of
+ * fosvos_conv3x3_wgrad_tc_accumulate);  ws = 0.   x_is_a = fosvos_conv3x3_wgrad_tc_orientation().
+ * repack: rebuild the packed bf16 copies of the VALID (co < Cout, ci < Cin) region -- the padding of
+ * buffers first filled by fosvos_pack_conv3x3_weight stays zero -- and the padded fp32 bias.
+ * `tile_prefix[e]` = sum over earlier entries of fosvos_{fold,repack}_tile_count(Cout, Cin); n_entries + 1 ints. */
+typedef struct fosvos_fold_entry {
+  float* ws;
+  float* dw;
+  int Cout, Cin, CoutP, CinP;
+  int x_is_a;
+  int pad_;
+} fosvos_fold_entry;
+typedef struct fosvos_repack_entry {
+  const float* w;      /* (Cout,Cin,3,3) fp32 */
+  const float* bias;   /* Cout fp32 or NULL */
+  void* out_fwd;       /* FOSVOS_W_TC_FWD bf16 or NULL */
+  void* out_dgrad;     /* FOSVOS_W_TC_DGRAD bf16 or NULL */
+  float* bias_out;     /* CoutP fp32 or NULL */
+  int Cout, Cin;
+  int pad_ci, pad_co;  /* K extents of the two packed layouts: ceil64(CinP), ceil64(CoutP) */
+} fosvos_repack_entry;
+int fosvos_conv3x3_wgrad_tc_orientation(int CinP, int CoutP);
+int fosvos_fold_tile_count(int Cout, int Cin);
+int fosvos_repack_tile_count(int Cout, int Cin);
+int fosvos_wgrad_fold_all(const fosvos_fold_entry* table, int n_entries, const int* tile_prefix,
+                          int n_tiles, fosvos_stream_t stream);
+int fosvos_repack_all(const fosvos_repack_entry* table, int n_entries, const int* tile_prefix,
+                      int n_tiles, fosvos_stream_t stream);
+
 /* ---- mask egress --------------------------------------------------------------------
  * counts (device, 2 x int64 per frame): intersection and union pixel counts of two uint8
  * {0,1} masks -- the integers of the DAVIS J (region IoU) measure. Zeroed by the call. */
