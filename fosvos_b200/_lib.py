@@ -43,6 +43,11 @@ SIGNATURES = {
     "fosvos_repack_tile_count": (_i, [_i, _i]),
     "fosvos_wgrad_fold_all": (_i, [_vp, _i, _vp, _i, _vp]),
     "fosvos_repack_all": (_i, [_vp, _i, _vp, _i, _vp]),
+    "fosvos_adam_chunk_elems": (_i, []),
+    "fosvos_adam_step": (_i, [_vp, _i, _vp, _i, C.c_float, C.c_float, C.c_float, _vp, _i, _vp]),
+    "fosvos_pixel_loss": (_i, [_vp, _vp, C.c_longlong, _i, _i, C.c_float, _vp, _vp, _vp]),
+    "fosvos_taylor_rank": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _vp]),
     "fosvos_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_maxpool2x2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_params_bytes": (C.c_size_t, []),

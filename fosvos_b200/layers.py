@@ -60,6 +60,33 @@ def class_balanced_cross_entropy_loss(output, label, size_average=True):
     return _BalancedLoss.apply(output, label, bool(size_average))
 
 
+class _PixelLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, target, kind, size_average):
+        L.require_device(output.device)
+        out32 = output.detach().to(torch.float32).contiguous()
+        tgt32 = target.detach().to(torch.float32).contiguous()
+        loss, dx = ops.pixel_loss(out32, tgt32, kind, size_average, 1.0, want_grad=True)
+        ctx.save_for_backward(dx)
+        ctx.out_shape, ctx.out_dtype = output.shape, output.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dx,) = ctx.saved_tensors
+        return (dx * grad_out).view(ctx.out_shape).to(ctx.out_dtype), None, None, None
+
+
+def mse_loss(output, target, size_average=False):
+    """``nn.MSELoss(size_average=False)`` of the distillation driver (reference mimic.py:76): one fused kernel."""
+    return _PixelLoss.apply(output, target, "mse", bool(size_average))
+
+
+def l1_loss(output, target, size_average=False):
+    """``nn.L1Loss(size_average=False)`` (reference mimic.py:79)."""
+    return _PixelLoss.apply(output, target, "l1", bool(size_average))
+
+
 def center_crop(x, height, width):
     """Negative-pad centre crop, reference osvos_layers.py:47-54 (left/top get ceil(-d/2))."""
     crop_h = -(x.size()[2] - height) / 2.0

@@ -190,15 +190,28 @@ class OSVOS_VGG(nn.Module):
         return self._side_params
 
     # ------------------------------------------------------------------ the path
+    #: BGR mean of the DAVIS loaders (reference dataloaders/davis_2016.py:24)
+    MEANVAL = (104.00699, 116.66877, 122.67892)
+
     def _run_forward(self, x: torch.Tensor, save: bool, want_prob: bool = False, want_mask: bool = False):
-        """NHWC pipeline.  Returns (outs, prob, mask, saved) ; saved holds what backward needs."""
+        """NHWC pipeline.  Returns (outs, prob, mask, saved) ; saved holds what backward needs.
+        ``x``: (N,3,H,W) fp32 mean-subtracted frames (the reference contract), or raw (N,H,W,3) uint8 frames as
+        cv2 delivers them -- mean subtraction and layout change then happen in one ingest kernel."""
         L.require_device(x.device)
+        if x.dtype == torch.uint8:
+            if x.dim() != 4 or x.shape[3] != 3 or self.stages[0][0].in_channels != 3:
+                raise RuntimeError(f"OSVOS_VGG: uint8 frames must be (N,H,W,3), got {tuple(x.shape)}")
+            return self._run_pipeline(ops.ingest_u8(x, self.MEANVAL, _act_dtype(self.precision)), int(x.shape[1]), int(x.shape[2]),
+                                      save, want_prob, want_mask)
         if x.dim() != 4 or x.shape[1] != self.stages[0][0].in_channels:
             raise RuntimeError(f"OSVOS_VGG.forward expects (N,{self.stages[0][0].in_channels},H,W), got {tuple(x.shape)}")
-        H, W = int(x.shape[-2]), int(x.shape[-1])
         dt = _act_dtype(self.precision)
         impl = self._impl()
-        a = ops.nchw_to_nhwc(x.float(), dt)
+        H, W = int(x.shape[-2]), int(x.shape[-1])
+        return self._run_pipeline(ops.nchw_to_nhwc(x.float(), dt), H, W, save, want_prob, want_mask)
+
+    def _run_pipeline(self, a: torch.Tensor, H: int, W: int, save: bool, want_prob: bool, want_mask: bool):
+        impl = self._impl()
         conv_in: List[torch.Tensor] = []        # input activation of every stage conv, in order
         conv_out: List[torch.Tensor] = []
         pool_in: List[Optional[torch.Tensor]] = []
@@ -227,11 +240,14 @@ class OSVOS_VGG(nn.Module):
         return outs, prob, mask, saved
 
     def _run_backward(self, saved, douts: Sequence[Optional[torch.Tensor]], grads: Dict[str, torch.Tensor],
-                      wgrad_ws: Optional[Dict[str, torch.Tensor]] = None) -> None:
+                      wgrad_ws: Optional[Dict[str, torch.Tensor]] = None,
+                      taylor: Optional[Dict[str, torch.Tensor]] = None) -> None:
         """Accumulate (+=) parameter gradients into ``grads`` (name -> fp32 tensor, reference layout).
         With ``wgrad_ws`` (conv name -> live accumulator, ``ops.wgrad_workspace``) the tensor-core weight
         gradients are left in their accumulators; the caller folds them into ``grads`` once per optimizer
-        step (``ops.conv3x3_wgrad_finish``)."""
+        step (``ops.conv3x3_wgrad_finish``).  With ``taylor`` (stage-conv name -> (Cout,) fp32) the pruning
+        criterion sum(activation * gradient) / (N H W) of every stage conv is accumulated on the way
+        (reference ``prune.py:163-178``; post-ReLU activation x masked gradient == the hooked product)."""
         if self._side_general:
             raise RuntimeError("fosvos_b200: backward through non-diagonal `upscale` weights is not supported "
                                "(the reference keeps them fixed with lr=0, network_provider.py:154-155)")
@@ -274,6 +290,8 @@ class OSVOS_VGG(nn.Module):
                 x_in = saved["conv_in"][k]
                 name = names[si][j]
                 wgrad(name, x_in, dz)
+                if taylor is not None and name in taylor:
+                    ops.taylor_rank(saved["conv_out"][k], dz, taylor[name])
                 if si == 0 and j == 0:
                     break
                 pc = self._packed_for(conv, need_dgrad=True)

@@ -22,6 +22,7 @@ from . import _lib as L
 from . import ops
 from .networks import OSVOS_VGG, _act_dtype
 from .optim import FusedSGD, get_optimizer_online
+from .sharding import allreduce_flat
 
 
 def _repack_in_place(net: OSVOS_VGG) -> None:
@@ -99,13 +100,23 @@ class OnlineTrainer:
     """
 
     def __init__(self, net: OSVOS_VGG, height: int, width: int, avg_grad_every_n: int = 5,
-                 optimizer: Optional[FusedSGD] = None, use_graph: bool = True, deep_supervision: Optional[float] = None):
+                 optimizer: Optional[FusedSGD] = None, use_graph: bool = True, deep_supervision: Optional[float] = None,
+                 data_parallel: bool = False, world_size: int = 1):
+        """``data_parallel``: offline parent training sharded over ``world_size`` ranks (one process per GPU): every
+        rank runs ``avg_grad_every_n // world_size`` micro-iterations on its own frames, gradients (scaled by
+        1/avg_grad_every_n as in the reference) are summed with ONE all-reduce of a flat fp32 buffer, then every
+        rank applies the same optimizer step."""
         dev = next(net.parameters()).device
         L.require_device(dev)
         self.net = net
-        self.n = int(avg_grad_every_n)
+        self.data_parallel = bool(data_parallel) and world_size > 1
+        if self.data_parallel and avg_grad_every_n % world_size != 0:
+            raise ValueError(f"avg_grad_every_n={avg_grad_every_n} must be a multiple of the world size {world_size}")
+        self.n = int(avg_grad_every_n) // (world_size if self.data_parallel else 1)      # micro-iterations per step on this rank
         self.scale = 1.0 / float(avg_grad_every_n)
         self.deep = deep_supervision
+        # the side-loss weight (1 - epoch / n_epochs, train_offline.py:88) lives on the device: captured graphs read it
+        self.deep_w = None if deep_supervision is None else torch.full((), float(deep_supervision), dtype=torch.float32, device=dev)
         self.optimizer = optimizer if optimizer is not None else get_optimizer_online(net)
         self.fused = isinstance(self.optimizer, FusedSGD)
         self.use_graph = bool(use_graph) and self.fused
@@ -113,6 +124,15 @@ class OnlineTrainer:
         self.mask = torch.zeros((1, 1, height, width), dtype=torch.float32, device=dev)
         params = dict(net.named_parameters())
         self.grads: Dict[str, torch.Tensor] = {}
+        self.flat_grad = None
+        if self.data_parallel:
+            names = net._grad_names()
+            self.flat_grad = torch.zeros(sum(params[n].numel() for n in names), dtype=torch.float32, device=dev)
+            off = 0
+            for name in names:
+                p = params[name]
+                p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+                off += p.numel()
         for name in net._grad_names():
             p = params[name]
             if p.grad is None:
@@ -144,11 +164,11 @@ class OnlineTrainer:
         loss, stats = ops.bal_loss_fwd(outs[4], self.mask, False)
         douts[4] = ops.bal_loss_bwd(outs[4], self.mask, False, stats, None, self.scale)
         total = loss
-        if self.deep is not None:
+        if self.deep_w is not None:
             for i in range(4):
                 li, st = ops.bal_loss_fwd(outs[i], self.mask, False)
-                douts[i] = ops.bal_loss_bwd(outs[i], self.mask, False, st, None, self.scale * self.deep)
-                total = total + self.deep * li
+                douts[i] = ops.bal_loss_bwd(outs[i], self.mask, False, st, self.deep_w, self.scale)
+                total = total + self.deep_w * li
         self.last_loss.copy_(total)
         self.loss_sum.add_(total)
         net._run_backward(saved, douts, self.grads, self.wgrad_ws)
@@ -160,8 +180,13 @@ class OnlineTrainer:
                                                   self.frame.device)
             ops.wgrad_fold_all(self._fold_table)
 
+    def set_deep_supervision(self, weight: float) -> None:
+        """New epoch: side-loss weight ``1 - epoch / n_epochs`` (train_offline.py:88); no re-capture needed."""
+        self.deep_w.fill_(float(weight))
+
     def _step(self) -> None:
-        self._fold_wgrads()
+        """optimizer.step(); optimizer.zero_grad() (+ re-packing).  The caller has folded the weight-gradient
+        accumulators (and all-reduced the gradients) before."""
         if self.fused:
             self.optimizer.step_and_zero()
             _repack_in_place(self.net)
@@ -243,6 +268,9 @@ class OnlineTrainer:
                 losses_out.append(float(self.last_loss.item()))
             self.counter += 1
             if self.counter % self.n == 0:
+                self._fold_wgrads()
+                if self.data_parallel:
+                    allreduce_flat(self.flat_grad)
                 if self.use_graph:
                     self._step_graph.replay()
                     L.CALLS[0] += self._calls_step

@@ -319,6 +319,68 @@ def sgd_step(table: torch.Tensor, prefix: torch.Tensor, n_tensors: int, n_chunks
                                     L.stream()), "sgd_step")
 
 
+# ---- Adam / distillation losses / pruning criterion / ingest ----------------------------
+ADAM_ENTRY = np.dtype([("p", np.uint64), ("g", np.uint64), ("m", np.uint64), ("v", np.uint64), ("n", np.int64),
+                       ("lr", np.float32), ("wd", np.float32)])
+
+
+def adam_table(entries, device):
+    """entries: (param, grad, exp_avg, exp_avg_sq, lr, weight_decay) -> (table, chunk_prefix, n_chunks) on device."""
+    chunk = L.lib().fosvos_adam_chunk_elems()
+    assert ADAM_ENTRY.itemsize == 48
+    tab = np.zeros(len(entries), dtype=ADAM_ENTRY)
+    prefix = np.zeros(len(entries) + 1, dtype=np.int64)
+    for i, (p, g, m, v, lr, wd) in enumerate(entries):
+        assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32
+        assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+        tab[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, wd)
+        prefix[i + 1] = prefix[i] + (p.numel() + chunk - 1) // chunk
+    return torch.from_numpy(tab.view(np.uint8).copy()).to(device), torch.from_numpy(prefix).to(device), int(prefix[-1])
+
+
+def adam_step(table: torch.Tensor, prefix: torch.Tensor, n_tensors: int, n_chunks: int, beta1: float, beta2: float, eps: float,
+              state: torch.Tensor, zero_grad: bool) -> None:
+    assert state.dtype == torch.int64 and state.numel() >= 1
+    L.check(L.lib().fosvos_adam_step(table.data_ptr(), n_tensors, prefix.data_ptr(), n_chunks, float(beta1), float(beta2), float(eps),
+                                     state.data_ptr(), int(zero_grad), L.stream()), "adam_step")
+
+
+def pixel_loss(output: torch.Tensor, target: torch.Tensor, kind: str, size_average: bool, grad_scale: float = 1.0,
+               want_grad: bool = True):
+    """nn.MSELoss ('mse') / nn.L1Loss ('l1') -> (loss 0-dim fp32, d loss / d output * grad_scale or None)"""
+    L.require_device(output.device)
+    assert output.dtype == torch.float32 and target.dtype == torch.float32 and output.numel() == target.numel()
+    output, target = output.contiguous(), target.contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=output.device)
+    dx = torch.empty_like(output) if want_grad else None
+    L.check(L.lib().fosvos_pixel_loss(output.data_ptr(), target.data_ptr(), output.numel(), {"mse": 0, "l1": 1}[kind],
+                                      int(size_average), float(grad_scale), loss.data_ptr(), L.ptr(dx), L.stream()), "pixel_loss")
+    return loss, dx
+
+
+def taylor_rank(act: torch.Tensor, grad: torch.Tensor, rank: torch.Tensor) -> None:
+    """rank (C fp32) += sum over pixels of act * grad / (N H W);  act, grad NHWC of the same dtype."""
+    L.require_device(act.device)
+    n, h, w, cp = act.shape
+    assert grad.shape == act.shape and grad.dtype == act.dtype and act.is_contiguous() and grad.is_contiguous()
+    assert rank.dtype == torch.float32 and rank.numel() <= cp
+    L.check(L.lib().fosvos_taylor_rank(act.data_ptr(), grad.data_ptr(), rank.data_ptr(), n, h, w, cp, rank.numel(),
+                                       L.dtype_code(act.dtype), L.stream()), "taylor_rank")
+
+
+def ingest_u8(img: torch.Tensor, mean, dtype: torch.dtype) -> torch.Tensor:
+    """uint8 (N,H,W,3) device frames (cv2 channel order) -> NHWC8 activations, mean-subtracted."""
+    import ctypes
+    L.require_device(img.device)
+    assert img.dtype == torch.uint8 and img.dim() == 4 and img.shape[3] == 3
+    img = img.contiguous()
+    n, h, w, _ = img.shape
+    y = torch.empty((n, h, w, 8), dtype=dtype, device=img.device)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    L.check(L.lib().fosvos_ingest_u8(img.data_ptr(), y.data_ptr(), n, h, w, m, L.dtype_code(dtype), L.stream()), "ingest_u8")
+    return y
+
+
 # ---- mask egress ------------------------------------------------------------------------------
 def sigmoid_threshold(logits: torch.Tensor, want_prob: bool = True, want_mask: bool = True):
     L.require_device(logits.device)

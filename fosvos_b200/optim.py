@@ -80,6 +80,69 @@ class FusedSGD(Optimizer):
         return self.step(zero_grad=True)
 
 
+class FusedAdam(Optimizer):
+    """torch.optim.Adam (no amsgrad; L2 weight decay) as ONE multi-tensor launch -- the optimizer of the reference's
+    distillation and post-pruning fine-tuning loops (``mimic.py:74`` lr 1e-3, ``prune.py`` fine_tune lr 1e-4, wd 2e-4).
+    State keys match torch (``exp_avg``, ``exp_avg_sq``); the step counter lives on the device so a captured
+    graph can replay the step."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        if len({(g["betas"], g["eps"]) for g in self.param_groups}) != 1:
+            raise ValueError("FusedAdam needs one (betas, eps) for all groups")
+        self._table = None
+        self._table_key = None
+        self._step_dev = None
+
+    def _entries(self):
+        ent = []
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                ent.append((p, p.grad, st["exp_avg"], st["exp_avg_sq"], float(g["lr"]), float(g["weight_decay"])))
+        return ent
+
+    def _ensure_table(self):
+        ent = self._entries()
+        key = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), lr, wd) for p, g, m, v, lr, wd in ent)
+        if key != self._table_key:
+            if ent:
+                dev = ent[0][0].device
+                L.require_device(dev)
+                self._table = ops.adam_table([(p.detach(), g, m, v, lr, wd) for p, g, m, v, lr, wd in ent], dev) + (len(ent),)
+                if self._step_dev is None:
+                    self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            else:
+                self._table = None
+            self._table_key = key
+        return ent
+
+    @torch.no_grad()
+    def step(self, closure=None, zero_grad: bool = False):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        ent = self._ensure_table()
+        if self._table is None:
+            return loss
+        table, prefix, n_chunks, n_tensors = self._table
+        g0 = self.param_groups[0]
+        ops.adam_step(table, prefix, n_tensors, n_chunks, g0["betas"][0], g0["betas"][1], g0["eps"], self._step_dev, zero_grad)
+        for p, *_ in ent:
+            torch.autograd.graph.increment_version(p)
+        return loss
+
+    def step_and_zero(self):
+        return self.step(zero_grad=True)
+
+
 def _groups(net, mode: str, learning_rate: float, weight_decay: float) -> List[dict]:
     lr, wd = learning_rate, weight_decay
     groups = [

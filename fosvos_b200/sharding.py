@@ -47,6 +47,13 @@ def sum_over_ranks(v: float, device="cuda") -> float:
     return float(t.item())
 
 
+def allreduce_flat(flat: torch.Tensor) -> None:
+    """Sum ONE flat fp32 gradient buffer over the ranks in place: the data-parallel exchange step of offline
+    parent training and distillation (61 MB per optimizer step for the full VGG; NCCL ring / NVLS over NVSwitch)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20) -> None:
     """Sum the fp32 gradients over ranks (data-parallel offline training / distillation):
     flat buckets of ~32 MB so a step's 61 MB payload is two NCCL launches; lr=0 tensors

@@ -248,6 +248,35 @@ int fosvos_wgrad_fold_all(const fosvos_fold_entry* table, int n_entries, const i
 int fosvos_repack_all(const fosvos_repack_entry* table, int n_entries, const int* tile_prefix,
                       int n_tiles, fosvos_stream_t stream);
 
+/* ---- callers either side of the path ----------------------------------------
+ * Adam with torch.optim.Adam semantics (mimic.py:74, prune.py fine_tune): g += wd*p; m,v EMA; bias-corrected
+ * update.  `state` = one device int64 step counter, incremented by the call (CUDA-graph friendly). */
+typedef struct fosvos_adam_entry {
+  float* p;
+  float* g;
+  float* m;
+  float* v;
+  long long n;
+  float lr;
+  float weight_decay;
+} fosvos_adam_entry;
+int fosvos_adam_chunk_elems(void);
+int fosvos_adam_step(const fosvos_adam_entry* table, int n_tensors, const long long* chunk_prefix,
+                     int n_chunks, float beta1, float beta2, float eps, long long* state,
+                     int zero_grad, fosvos_stream_t stream);
+/* nn.MSELoss (kind 0) / nn.L1Loss (kind 1) of two fp32 maps, forward and gradient in one pass
+ * (mimic.py:76-81): *loss = sum or mean;  dx (may be NULL) = grad_scale * d loss / d output. */
+int fosvos_pixel_loss(const float* output, const float* target, long long numel, int kind,
+                      int size_average, float grad_scale, float* loss, float* dx,
+                      fosvos_stream_t stream);
+/* Taylor pruning criterion (prune.py:163-178): rank[c] += sum_p act[p,c]*grad[p,c] / (N*H*W). NHWC. */
+int fosvos_taylor_rank(const void* act, const void* grad, float* rank, int N, int H, int W, int CP,
+                       int C, int dtype, fosvos_stream_t stream);
+/* Frame ingest (dataloaders/davis_2016.py:115-128 + ToTensor): device uint8 (N,H,W,3) as cv2 delivers it
+ * -> (N,H,W,8) activations, channel c = img[c] - mean3[c] (mean3: 3 HOST floats), channels 3..7 zero. */
+int fosvos_ingest_u8(const uint8_t* img, void* y_nhwc8, int N, int H, int W, const float* mean3,
+                     int dtype, fosvos_stream_t stream);
+
 /* ---- mask egress --------------------------------------------------------------------
  * counts (device, 2 x int64 per frame): intersection and union pixel counts of two uint8
  * {0,1} masks -- the integers of the DAVIS J (region IoU) measure. Zeroed by the call. */

@@ -127,13 +127,16 @@ def test_bench_sharding_two_ranks_gloo(tmp_path):
     script.write_text(
         "import os, sys, torch, torch.distributed as dist\n"
         f"sys.path.insert(0, {ROOT!r})\n"
-        "from fosvos_b200.sharding import init_distributed, max_over_ranks, sum_over_ranks\n"
+        "from fosvos_b200.sharding import init_distributed, max_over_ranks, sum_over_ranks, allreduce_flat\n"
         "from fosvos_b200 import sequences_for_rank\n"
         "rank, world = init_distributed(backend='gloo')\n"
         "mine = sequences_for_rank(list(range(5)), rank, world)\n"
         "t = max_over_ranks(float(10 + rank), device='cpu')\n"
         "n = sum_over_ranks(float(len(mine)), device='cpu')\n"
         "assert t == 11.0 and n == 5.0, (t, n)\n"
+        "flat = torch.arange(6, dtype=torch.float32) * (rank + 1)\n"
+        "allreduce_flat(flat)          # the data-parallel gradient exchange of offline training / distillation\n"
+        "assert torch.equal(flat, torch.arange(6, dtype=torch.float32) * 3), flat\n"
         "open(os.path.join(os.path.dirname(__file__), f'rank{rank}.txt'), 'w').write(repr(mine))\n"
         "dist.destroy_process_group()\n")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
