@@ -33,6 +33,7 @@ SIGNATURES = {
     "fosvos_pad_bias": (_i, [_vp, _vp, _i, _i, _vp]),
     "fosvos_conv3x3_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_conv3x3_tc_pool": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_simt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_tc_workspace_bytes": (C.c_size_t, [_i, _i]),
     "fosvos_conv3x3_wgrad_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -85,6 +85,7 @@ struct TcParams {
   const float* bias;             // CoutP fp32 or null
   const __nv_bfloat16* mask;     // (N,H,W,CoutP) or null
   __nv_bfloat16* y;              // (N,H,W,CoutP)
+  __nv_bfloat16* y_pool;         // (N,ceil(H/2),ceil(W/2),CoutP) or null: 2x2/2 ceil-mode max pool of y, fused (ReLU outputs only)
   const __nv_bfloat16* w;        // packed weight (MODE_C8 reads it directly)
   int N, H, W, CoutP;
   int tiles_x, tiles_y, n_tiles_n, total_tiles;
@@ -431,6 +432,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 for (int q = 0; q < 4; ++q) packed[4 * h + q] = ptx::cvt_bf16x2(v[2 * q], v[2 * q + 1]);
               }
             }
+            if (p.y_pool) {
+              // nn.MaxPool2d(2, 2, ceil_mode=True) on the way out (osvos_vgg.py:90).  A warp holds whole image rows of
+              // the patch, so the 2x2 partners are lanes +1 and +TW.  Out-of-frame pixels count as 0: the values are
+              // post-ReLU, so a zero never wins against an in-frame value and ceil-mode windows come out right.
+              uint32_t m[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t mine = in_img ? packed[i] : 0u;
+                const uint32_t right = __shfl_down_sync(0xffffffffu, mine, 1);
+                __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&mine), *reinterpret_cast<const __nv_bfloat162*>(&right));
+                const uint32_t am = *reinterpret_cast<uint32_t*>(&a);
+                const uint32_t below = __shfl_down_sync(0xffffffffu, am, TW);
+                __nv_bfloat162 b = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(&below));
+                m[i] = *reinterpret_cast<uint32_t*>(&b);
+              }
+              if (in_img && !(px & 1) && !(py & 1)) {
+                const int PH = (p.H + 1) >> 1, PW = (p.W + 1) >> 1;
+                __nv_bfloat16* dst = p.y_pool + (((long long)n * PH + (gy >> 1)) * PW + (gx >> 1)) * p.CoutP + co0 + 32 * half;
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                  if (co0 + 32 * half + 8 * h < p.CoutP)
+                    *reinterpret_cast<uint4*>(dst + 8 * h) = make_uint4(m[4 * h], m[4 * h + 1], m[4 * h + 2], m[4 * h + 3]);
+              }
+            }
           }
           if (j == SLABS - 1) {                           // all TMEM reads of this tile are done: hand the accumulator back
             ptx::tc_fence_before();
@@ -614,8 +639,8 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   return check_launch("conv3x3_tc");
 }
 
-static int conv_tc_common(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, int N, int H,
-                          int W, int Cin, int Cout, int taps, int flags, fosvos_stream_t stream, const char* what) {
+static int conv_tc_common(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, int N,
+                          int H, int W, int Cin, int Cout, int taps, int flags, fosvos_stream_t stream, const char* what) {
   FOSVOS_REQUIRE(x && w_packed && y && N > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", what);
   FOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin > 0 && Cout > 0,
                  "%s: Cin=%d and Cout=%d must be positive multiples of 8 (pad the NHWC tensors)", what, Cin, Cout);
@@ -627,6 +652,7 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   p.bias = bias;
   p.mask = (const __nv_bfloat16*)mask;
   p.y = (__nv_bfloat16*)y;
+  p.y_pool = (__nv_bfloat16*)y_pool;
   p.w = (const __nv_bfloat16*)w_packed;
   p.N = N; p.H = H; p.W = W; p.CoutP = Cout;
   const bool c8 = taps == 9 && Cin == 8 && Cout <= 64 && !getenv("FOSVOS_TC_NO_C8");
@@ -700,7 +726,16 @@ extern "C" {
 
 int fosvos_conv3x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, int N, int H,
                       int W, int Cin, int Cout, int flags, fosvos_stream_t stream) {
-  return conv_tc_common(x, w_packed, bias, mask, y, N, H, W, Cin, Cout, 9, flags, stream, "conv3x3_tc");
+  return conv_tc_common(x, w_packed, bias, mask, y, nullptr, N, H, W, Cin, Cout, 9, flags, stream, "conv3x3_tc");
+}
+
+int fosvos_conv3x3_tc_pool(const void* x, const void* w_packed, const float* bias, void* y, void* y_pool, int N, int H, int W,
+                           int Cin, int Cout, int flags, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(y_pool, "conv3x3_tc_pool: y_pool is null");
+  FOSVOS_REQUIRE((flags & FOSVOS_CONV_RELU) && !(flags & (FOSVOS_CONV_MASK | FOSVOS_CONV_ACCUMULATE)),
+                 "conv3x3_tc_pool: the fused pool needs the RELU epilogue (non-negative values) and no mask/accumulate");
+  FOSVOS_REQUIRE(Cout >= 64 && ((uintptr_t)y_pool & 15) == 0, "conv3x3_tc_pool: Cout=%d must be >= 64 (slab epilogue), y_pool 16-byte aligned", Cout);
+  return conv_tc_common(x, w_packed, bias, nullptr, y, y_pool, N, H, W, Cin, Cout, 9, flags, stream, "conv3x3_tc_pool");
 }
 
 }  // extern "C"

@@ -68,6 +68,7 @@ class OSVOS_VGG(nn.Module):
         self._initialize_weights(pretrained)
 
         self.precision = os.environ.get("FOSVOS_PRECISION", "bf16")
+        self.fuse_pool = os.environ.get("FOSVOS_FUSE_POOL", "1") != "0"    # max pool written by the producing conv's epilogue
         self._packed: Dict[int, _PackedConv] = {}
         self._side_key = None
         self._side_params: Optional[torch.Tensor] = None
@@ -217,14 +218,20 @@ class OSVOS_VGG(nn.Module):
         pool_in: List[Optional[torch.Tensor]] = []
         stage_out: List[torch.Tensor] = []
         sps: List[torch.Tensor] = []
+        pooled: Optional[torch.Tensor] = None   # the next stage's input when the pool rode along in the conv epilogue
         for si, convs in enumerate(self._stage_convs()):
             if si > 0:
                 pool_in.append(a)
-                a = ops.maxpool2x2(a)
-            for conv in convs:
+                a = pooled if pooled is not None else ops.maxpool2x2(a)
+                pooled = None
+            for ci, conv in enumerate(convs):
                 pc = self._packed_for(conv, need_dgrad=save)
                 conv_in.append(a)
-                a = ops.conv3x3(a, pc.w_fwd, pc.bias, ops.pad8(conv.out_channels), L.CONV_BIAS | L.CONV_RELU, impl=impl)
+                cp = ops.pad8(conv.out_channels)
+                if impl == "tc" and si < 4 and ci == len(convs) - 1 and cp >= 64 and a.shape[3] > 8 and self.fuse_pool:
+                    a, pooled = ops.conv3x3_pool(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU)
+                else:
+                    a = ops.conv3x3(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU, impl=impl)
                 conv_out.append(a)
             stage_out.append(a)
             if si > 0:

@@ -85,6 +85,19 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+def conv3x3_pool(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout_p: int, flags: int):
+    """tcgen05 conv + ReLU with the following 2x2/2 ceil-mode max pool written from the same epilogue
+    -> (y (N,H,W,C), pooled (N,ceil(H/2),ceil(W/2),C))."""
+    L.require_device(x.device)
+    n, h, w, cin_p = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    y = torch.empty((n, h, w, cout_p), dtype=x.dtype, device=x.device)
+    yp = torch.empty((n, (h + 1) // 2, (w + 1) // 2, cout_p), dtype=x.dtype, device=x.device)
+    L.check(L.lib().fosvos_conv3x3_tc_pool(x.data_ptr(), w_packed.data_ptr(), L.ptr(bias), y.data_ptr(), yp.data_ptr(),
+                                           n, h, w, cin_p, cout_p, flags, L.stream()), "conv3x3_tc_pool")
+    return y, yp
+
+
 def wgrad_workspace(cin_p: int, cout_p: int, device) -> torch.Tensor:
     """Zeroed [tap][M][N] fp32 accumulator of the tensor-core weight gradient (kept live across micro-iterations)."""
     return torch.zeros(L.lib().fosvos_conv3x3_wgrad_tc_workspace_bytes(cin_p, cout_p) // 4, dtype=torch.float32, device=device)

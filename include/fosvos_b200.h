@@ -110,6 +110,12 @@ int fosvos_conv3x3_simt(const void* x, const void* w_packed, const float* bias, 
 int fosvos_conv3x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
                       void* y, int N, int H, int W, int Cin, int Cout, int flags,
                       fosvos_stream_t stream);
+/* Same, and additionally y_pool (N,ceil(H/2),ceil(W/2),Cout) = nn.MaxPool2d(2,2,ceil_mode=True)(y)
+ * (osvos_vgg.py:90) written from the same epilogue.  Needs FOSVOS_CONV_RELU (values >= 0), Cout >= 64,
+ * no MASK / ACCUMULATE. */
+int fosvos_conv3x3_tc_pool(const void* x, const void* w_packed, const float* bias, void* y,
+                           void* y_pool, int N, int H, int W, int Cin, int Cout, int flags,
+                           fosvos_stream_t stream);
 
 /* weight + bias gradient of the same convolution (autograd convolution_backward,
  * train_online.py:93):  dw[co,ci,r,s] += sum_p x[p+tap,ci] * dz[p,co];  db[co] += sum_p dz[p,co]

@@ -105,6 +105,25 @@ def test_conv3x3_forward(case, mode):
     assert (y[..., cout:] == 0).all()
 
 
+@pytest.mark.parametrize("case", [(1, 33, 45, 64, 64), (2, 16, 24, 64, 128), (1, 31, 70, 128, 256), (1, 9, 17, 40, 72)])
+def test_conv3x3_fused_maxpool(case):
+    """The producing conv's epilogue also writes MaxPool2d(2, 2, ceil_mode=True) of its ReLU output (odd sizes: the
+    last window is one pixel wide / high): bit-identical to the separate pool kernel."""
+    n, h, w_, cin, cout = case
+    g = _gen(51)
+    x = _nhwc(torch.randn(n, cin, h, w_, generator=g), torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, generator=g).to(DEV) * 0.05
+    b = torch.randn(cout, generator=g).to(DEV)
+    wp = ops.pack_weight(w, L.W_TC_FWD, torch.bfloat16)
+    bp = ops.pad_bias(b, cout, DEV)
+    cp = ops.pad8(cout)
+    y_ref = ops.conv3x3(x, wp, bp, cp, L.CONV_BIAS | L.CONV_RELU)
+    p_ref = ops.maxpool2x2(y_ref)
+    y, yp = ops.conv3x3_pool(x, wp, bp, cp, L.CONV_BIAS | L.CONV_RELU)
+    assert torch.equal(y, y_ref)
+    assert torch.equal(yp, p_ref)
+
+
 @pytest.mark.parametrize("impl,dt", [("simt", torch.float32), ("tc", torch.bfloat16)])
 def test_conv3x3_mask_accumulate_dgrad(impl, dt):
     """The data-gradient use of the kernel: flipped/transposed weights, ReLU mask, += fan-in."""
