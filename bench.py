@@ -124,6 +124,11 @@ def run_ours(args):
     frames_h, masks_h = make_sequence_gpu(rank, args.frames)
     frames_pin, masks_pin = frames_h.pin_memory(), masks_h.pin_memory()
     frames_d, masks_d = frames_h.to(dev), masks_h.to(dev)
+    # the raw frames a loader holds: uint8 HWC (cv2 order); frame = uint8 - mean exactly (davis_2016.py:127-128)
+    mean = torch.tensor(FB.OSVOS_VGG.MEANVAL, dtype=torch.float32).view(1, 3, 1, 1)
+    frames_u8 = (frames_h + mean).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(frames_u8.permute(0, 3, 1, 2).float() - mean, frames_h), "synthetic frames are uint8 - mean"
+    frames_u8_pin = frames_u8.pin_memory()
 
     def new_net():
         net = FB.OSVOS_VGG(pretrained=0)
@@ -156,7 +161,8 @@ def run_ours(args):
         e[1].record()
         out_masks = []
         for i in range(0, args.frames, args.batch):
-            fb = frames_pin[i:i + args.batch].to(dev, non_blocking=True) if host else frames_d[i:i + args.batch]
+            # end to end: raw uint8 frames cross PCIe (4x fewer bytes), mean subtraction + layout happen in the ingest kernel
+            fb = frames_u8_pin[i:i + args.batch].to(dev, non_blocking=True) if host else frames_d[i:i + args.batch]
             _, _, mask = net.predict(fb)
             if host:
                 masks_out_pin[i:i + args.batch].copy_(mask, non_blocking=True)     # D2H of the result
@@ -196,7 +202,7 @@ def run_ours(args):
     torch.cuda.synchronize(); sharding.barrier()
     te = sharding.max_over_ranks(te)
     e2e = dict(value=total_frames / (te / 1e3), unit="frames/s",
-               h2d_bytes_per_step=int(args.frames * 3 * H * W * 4 + 4 * H * W * 4),
+               h2d_bytes_per_step=int(args.frames * 3 * H * W + 4 * H * W * 4),      # uint8 frames + the fp32 annotated frame and mask
                d2h_bytes_per_step=int(args.frames * H * W))
 
     out = None
@@ -204,6 +210,7 @@ def run_ours(args):
         # ---- roofline of the dominant kernel family (3x3 conv implicit GEMM), measured live -------
         roof = conv_roofline(new_net(), frames_d[:args.batch], peaks, args.precision)
         side = side_roofline(new_net(), frames_d[:args.batch], peaks)
+        loss_roof = loss_roofline(args.batch, dev, peaks)
         cpu = cpu_baseline(sd0, frames_h, masks_h, args)
         out = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -216,7 +223,7 @@ def run_ours(args):
             "inference_fps": world * args.steps * args.frames / (t_inf_max / 1e3),
             "finetune_s_per_sequence": t_ft_max / 1e3 / args.steps,
             "finetune_tflops": ITER_GFLOP * args.iters * args.steps / (t_ft_max / 1e3) / 1e3 if t_ft_max > 0 else None,
-            "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks, "roofline": roof, "roofline_side_chain": side,
+            "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks, "roofline": roof, "roofline_side_chain": side, "roofline_loss": loss_roof,
             "cpu_baseline": cpu, "peaks": peaks,
         }
         print(json.dumps(out), flush=True)
@@ -287,6 +294,23 @@ def side_roofline(net, frames, peaks):
     achieved = bytes_per_frame * n / (ms / 1e3) / 1e9
     return dict(bound="hbm", kernel="side_heads_kernel + side_upsample_kernel", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                 frac=achieved / peaks["hbm_gbs"], traffic=None, batch=n, ms=ms, bytes_per_frame=bytes_per_frame)
+
+
+def loss_roofline(n, dev, peaks):
+    """HBM roofline of the class-balanced loss: forward reduction (8 B/px) + backward (12 B/px) on n label maps."""
+    from fosvos_b200 import ops
+    x = torch.randn((n, 1, H, W), device=dev)
+    lab = (torch.rand((n, 1, H, W), device=dev) > 0.8).float()
+    dx = torch.empty_like(x)
+    _, stats = ops.bal_loss_fwd(x, lab, False)
+    def run():
+        _, st = ops.bal_loss_fwd(x, lab, False)
+        ops.bal_loss_bwd(x, lab, False, st, None, 1.0, out=dx)
+    ms = _time_ms(run, reps=10)
+    b = 20 * x.numel()
+    achieved = b / (ms / 1e3) / 1e9
+    return dict(bound="hbm", kernel="bal_loss_fwd_kernel + bal_loss_bwd_kernel", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
+                frac=achieved / peaks["hbm_gbs"], traffic=None, batch=n, ms=ms, bytes_per_frame=20 * H * W)
 
 
 def cpu_baseline(sd, frames, masks, args, forward_frames=2, ft_iters=1):
