@@ -18,9 +18,9 @@
 // [tap][M][N] workspace; `wgrad_unpack_kernel` then adds it into the OIHW fp32 .grad tensor.  The
 // workspace may stay live across micro-iterations (`_accumulate` / `_finish`), so the unpack runs once
 // per optimizer step.
-// Bias gradient db[co] = sum_p dZ[p][co]: the dZ boxes are in shared memory anyway, so in the CTAs that
-// see every (pixel, cout) exactly once (s == 0 and the first tile of the X-channel dimension) the four
-// epilogue warps, otherwise idle until the accumulators are complete, sum them on the side.
+// Bias gradient db[co] = sum_p dZ[p][co]: the dZ boxes are in shared memory anyway, so the four epilogue
+// warps, otherwise idle until the accumulators are complete, sum them on the side; the CTAs that see the
+// same dZ tile (three kernel columns x the tiles of the X-channel dimension) take every share-th patch each.
 #include <stdlib.h>
 
 #include <mutex>
@@ -47,6 +47,7 @@ struct WgParams {
   int x_is_a;
   int stages, stage_bytes, a_bytes;
   int x_block;               // bytes of one shifted 64-channel box: (TH+2)*TW*128
+  int debug;                 // FOSVOS_WG_DEBUG: 1 = skip the reductions (timing experiments only), 2 = no start rotation
 };
 
 // MN-major SWIZZLE_128B operand: rows (K) of 128 B, 8-row groups SBO = 1024 B apart, 64-element
@@ -81,8 +82,12 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const int s = item % 3; item /= 3;
   const int nt = item % p.n_tiles;
   const int mt = item / p.n_tiles;
-  // this CTA also sums dZ over its pixels (see the header comment)
-  const bool do_bias = p.db != nullptr && s == 0 && (p.x_is_a ? mt == 0 : nt == 0);
+  // Bias gradient: the CTAs (s, other-dimension tile) that share this CTA's dZ tile split its patches between them
+  // (patch pt belongs to CTA pt % share == share_id), so the extra shared-memory reads are spread evenly instead of
+  // slowing one CTA in three -- the MMA stream already uses the full shared-memory bandwidth.
+  const bool do_bias = p.db != nullptr;
+  const int share = 3 * (p.x_is_a ? p.m_tiles : p.n_tiles);
+  const int share_id = s * (p.x_is_a ? p.m_tiles : p.n_tiles) + (p.x_is_a ? mt : nt);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform roles
   if (warp == 0 && lane == 0) {
@@ -190,9 +195,10 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       for (int pt = p_begin; pt < p_end; ++pt) {
         ptx::mbar_wait(&full_bar[stage], phase);
         const uint8_t* zb = smem + stage * p.stage_bytes + z_off + off;
+        const bool mine = (pt % share) == share_id;
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-          if (b < nb_z) {
+          if (mine && b < nb_z) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint4 v = *reinterpret_cast<const uint4*>(zb + b * WG_PLAIN_BLOCK + j * 2048);
@@ -213,20 +219,24 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       for (int b = 0; b < 2; ++b)
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(&bias_red[b * 64 + c * 8 + e], acc[b][e]);
-      ptx::named_bar_sync(1, 128);
-      if (zc0 + t < p.cout && t < 64 * nb_z) atomicAdd(p.db + zc0 + t, bias_red[t]);
     }
     if (p_end > p_begin) {
       ptx::mbar_wait(done_bar, 0);
       ptx::tc_fence_after();
-      const bool row_ok = (m0 + row) < p.Mtot;
+      const bool row_ok = (m0 + row) < p.Mtot && p.debug != 1;
+      // the splits of one tile finish together and add into the same addresses: start each at a different
+      // (kernel row, column block) so that concurrent reductions mostly hit different L2 lines
+      const int rot = p.debug == 2 ? 0 : split;
+      const int n_cb = p.n_cols >> 4;
 #pragma unroll 1
-      for (int r = 0; r < 3; ++r) {
+      for (int rr = 0; rr < 3; ++rr) {
+        const int r = (rr + rot) % 3;
         const int tap = r * 3 + s;
         float* dst = p.ws + ((long long)tap * p.Mtot + (m0 + row)) * p.Ntot + n0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * p.n_cols;
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.n_cols; c0 += 16) {
+        for (int cb = 0; cb < n_cb; ++cb) {
+          const int c0 = ((cb + rot / 3) % n_cb) << 4;
           uint32_t v[16];
           ptx::tmem_ld16(taddr + c0, v);
           ptx::tmem_ld_wait();
@@ -240,6 +250,12 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           }
         }
       }
+    }
+    if (do_bias) {
+      // last, off the critical path: this CTA's share of the bias gradient (its shared-memory partial sums are complete)
+      ptx::named_bar_sync(1, 128);
+      const int t = threadIdx.x - 64;
+      if (zc0 + t < p.cout && t < 64 * nb_z) atomicAdd(p.db + zc0 + t, bias_red[t]);
     }
   }
   ptx::tc_fence_before();
@@ -362,6 +378,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   if (const char* e = getenv("FOSVOS_WG_SPLITS")) { const int v = atoi(e); if (v > 0) splits = v; }
   splits = min(splits, p.patches);
   p.splits = splits;
+  { const char* e = getenv("FOSVOS_WG_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
   CUtensorMap mx, mz;
   int rc = wg_encode(&mx, x, N, H, W, CinP, TW, TH + 2);

@@ -69,6 +69,10 @@ class OSVOS_VGG(nn.Module):
 
         self.precision = os.environ.get("FOSVOS_PRECISION", "bf16")
         self.fuse_pool = os.environ.get("FOSVOS_FUSE_POOL", "1") != "0"    # max pool written by the producing conv's epilogue
+        # side_prep convs and weight gradients are off the critical dependency chain: issue them on a second stream so
+        # their launch gaps, prologues and tail waves overlap the next layer (also inside captured CUDA graphs)
+        self.overlap = os.environ.get("FOSVOS_OVERLAP", "1") != "0"
+        self._side_stream: Optional[torch.cuda.Stream] = None
         self._packed: Dict[int, _PackedConv] = {}
         self._side_key = None
         self._side_params: Optional[torch.Tensor] = None
@@ -211,8 +215,17 @@ class OSVOS_VGG(nn.Module):
         H, W = int(x.shape[-2]), int(x.shape[-1])
         return self._run_pipeline(ops.nchw_to_nhwc(x.float(), dt), H, W, save, want_prob, want_mask)
 
+    def _aux_stream(self, device) -> Optional[torch.cuda.Stream]:
+        if not self.overlap:
+            return None
+        if self._side_stream is None or self._side_stream.device != device:
+            self._side_stream = torch.cuda.Stream(device=device)
+        return self._side_stream
+
     def _run_pipeline(self, a: torch.Tensor, H: int, W: int, save: bool, want_prob: bool, want_mask: bool):
         impl = self._impl()
+        main = torch.cuda.current_stream(a.device)
+        aux = self._aux_stream(a.device)
         conv_in: List[torch.Tensor] = []        # input activation of every stage conv, in order
         conv_out: List[torch.Tensor] = []
         pool_in: List[Optional[torch.Tensor]] = []
@@ -237,7 +250,19 @@ class OSVOS_VGG(nn.Module):
             if si > 0:
                 sp_conv = self.side_prep[si - 1]
                 pc = self._packed_for(sp_conv, need_dgrad=save)
-                sps.append(ops.conv3x3(a, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, impl=impl))
+                if aux is None:
+                    sps.append(ops.conv3x3(a, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, impl=impl))
+                else:
+                    # output allocated on the main stream (its pool), written on the auxiliary one
+                    sp = torch.empty((a.shape[0], a.shape[1], a.shape[2], 16), dtype=a.dtype, device=a.device)
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    aux.wait_event(ev)
+                    with torch.cuda.stream(aux):
+                        ops.conv3x3(a, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, out=sp, impl=impl)
+                    sps.append(sp)
+        if aux is not None:
+            main.wait_stream(aux)
         params = self._side()
         outs, prob, mask = ops.side_fwd(sps, params, H, W, general=self._side_general, want_prob=want_prob, want_mask=want_mask)
         saved = None
@@ -265,13 +290,29 @@ class OSVOS_VGG(nn.Module):
             douts = list(douts)
             douts[4] = torch.zeros_like(next(d for d in douts if d is not None))
         g = lambda k: grads.get(k)  # noqa: E731
+        dev = sps[0].device
+        main = torch.cuda.current_stream(dev)
+        aux = self._aux_stream(dev)
+        keep = []          # operands of in-flight weight gradients: not released before the streams join
 
         def wgrad(name: str, x_in: torch.Tensor, dz: torch.Tensor) -> None:
             impl_w = self._wgrad_impl(x_in.shape[3])
-            if wgrad_ws is not None and impl_w == "tc":
-                ops.conv3x3_wgrad_accumulate(x_in, dz, wgrad_ws[name], g(name + ".bias"), grads[name + ".weight"].shape[0])
-            else:
-                ops.conv3x3_wgrad(x_in, dz, grads[name + ".weight"], g(name + ".bias"), impl=impl_w)
+
+            def run():
+                if wgrad_ws is not None and impl_w == "tc":
+                    ops.conv3x3_wgrad_accumulate(x_in, dz, wgrad_ws[name], g(name + ".bias"), grads[name + ".weight"].shape[0])
+                else:
+                    ops.conv3x3_wgrad(x_in, dz, grads[name + ".weight"], g(name + ".bias"), impl=impl_w)
+
+            if aux is None:
+                run()
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)            # dz (and x_in) are complete on the main stream here
+            aux.wait_event(ev)
+            with torch.cuda.stream(aux):
+                run()
+            keep.append((x_in, dz))
 
         dsp = ops.side_bwd(sps, saved["params"], douts, H, W, g("fuse.weight"), g("fuse.bias"),
                            [g(f"score_dsn.{i}.weight") for i in range(4)], [g(f"score_dsn.{i}.bias") for i in range(4)])
@@ -306,6 +347,9 @@ class OSVOS_VGG(nn.Module):
                 dz = ops.conv3x3(dz, pc.w_dgrad, None, x_in.shape[3], L.CONV_MASK, mask=x_in, impl=impl)
             if si > 0:
                 dA = ops.maxpool2x2_bwd(saved["pool_in"][si - 1], dz)
+        if aux is not None:
+            main.wait_stream(aux)
+        keep.clear()
 
     def _grad_names(self) -> List[str]:
         return [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("upscale")]
