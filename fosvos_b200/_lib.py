@@ -51,13 +51,16 @@ SIGNATURES = {
     "fosvos_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _vp]),
     "fosvos_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_maxpool2x2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_maxpool2x2_bwd_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_params_bytes": (C.c_size_t, []),
     "fosvos_side_workspace_bytes": (C.c_size_t, [_vp, _vp, _i]),
     "fosvos_side_prepare": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fosvos_side_check_diagonal": (_i, [_vp, _vp, _vp]),
     "fosvos_side_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fosvos_bal_loss_stats_bytes": (C.c_size_t, []),
     "fosvos_bal_loss_fwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp]),
+    "fosvos_bal_loss_fwd_bwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _f, _vp, _vp]),
     "fosvos_bal_loss_bwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _f, _vp, _vp]),
     "fosvos_sgd_chunk_elems": (_i, []),
     "fosvos_sgd_step": (_i, [_vp, _i, _vp, _i, _f, _i, _vp]),

@@ -56,6 +56,7 @@ constexpr int TC_BIAS_BYTES = 2048;  // all CoutP <= 512 biases, staged once per
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one 64-channel output slab of a tile
 constexpr int MODE_GENERIC = 0, MODE_C8 = 1, MODE_HALO = 2;
+constexpr int TC_FLAG_MASK_IN_REGS = 1 << 20;    // internal (FOSVOS_TC_MASK_REGS=1): apply the ReLU mask in the register phase
 constexpr int HALO_A_BYTES = 20 * 1024;          // (TH+2) x TW x 128 B: 18 KB for 16x8 patches, 20 KB for 8x16
 constexpr int C8_ROW_BYTES = (8 + 2) * 16;       // one image row of the halo tile: 10 pixels x 8 channels
 constexpr int C8_BOX_BYTES = (16 + 2) * C8_ROW_BYTES;   // 2880
@@ -363,7 +364,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint8_t* buf = staging + grp * TC_SLAB_BYTES;
     const int as = grp;
     const bool relu = (p.flags & FOSVOS_CONV_RELU) != 0;
-    const bool post = (p.flags & (FOSVOS_CONV_MASK | FOSVOS_CONV_ACCUMULATE)) != 0;
+    // MASK alone (the data gradient) is applied to the staged slab with coalesced loads, see below; the register
+    // path handles it only together with ACCUMULATE (one rounding of mask(acc) + old)
+    const bool post = (p.flags & (FOSVOS_CONV_ACCUMULATE | TC_FLAG_MASK_IN_REGS)) != 0;
+    const bool mask_slab = Cfg::STAGED && (p.flags & FOSVOS_CONV_MASK) && !post;
     int it = grp;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int nt = tile % p.n_tiles_n;
@@ -470,6 +474,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             for (int c = 0; c < 4; ++c)
               *reinterpret_cast<uint4*>(rowp + (((4 * half + c) ^ (row & 7)) << 4)) =
                   make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            if (mask_slab) {
+              // ReLU backward on the staged slab: thread -> (16-byte chunk c, pixel rows rw, rw + 32, ...), so a warp reads
+              // four pixels x 128 contiguous bytes of the mask (= the layer input's post-ReLU activation): x != 0 <=> x > 0
+              ptx::named_bar_sync(bar_a, GRP_THREADS);
+              const int tg = threadIdx.x - 64 - grp * GRP_THREADS;
+              const int c = tg & 7;
+              if (co0 + 8 * c < p.CoutP) {
+#pragma unroll
+                for (int jj = 0; jj < TC_BM / (GRP_THREADS / 8); ++jj) {
+                  const int rw = (tg >> 3) + jj * (GRP_THREADS / 8);
+                  const int my = y0 + (rw >> p.tw_shift), mx = x0 + (rw & (TW - 1));
+                  if (mx < p.W && my < p.H) {
+                    const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.mask + (((long long)n * p.H + my) * p.W + mx) * p.CoutP + co0 + 8 * c));
+                    uint4* sp = reinterpret_cast<uint4*>(buf + rw * 128 + ((c ^ (rw & 7)) << 4));
+                    uint4 v = *sp;
+                    v.x &= __vcmpne2(mk.x, 0u); v.y &= __vcmpne2(mk.y, 0u); v.z &= __vcmpne2(mk.z, 0u); v.w &= __vcmpne2(mk.w, 0u);
+                    *sp = v;
+                  }
+                }
+              }
+            }
             ptx::fence_proxy_async_smem();
             ptx::named_bar_sync(bar_b, GRP_THREADS);
             if (issuer) {
@@ -666,7 +691,8 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   p.k_chunks = ceil_div(Cin, TC_BK);
   p.cin_pad = p.k_chunks * TC_BK;
   p.taps = taps;
-  p.flags = flags;
+  p.flags = flags & 0xffff;
+  if ((flags & FOSVOS_CONV_MASK) && getenv("FOSVOS_TC_MASK_REGS")) p.flags |= TC_FLAG_MASK_IN_REGS;
   const long long m_tiles = (long long)N * p.tiles_x * p.tiles_y;
   // N tile: minimise waves x cycles per tile.  One M=128 tcgen05.mma costs max(N/2, ~57) cycles
   // (tools/exp/mma_issue.cu), so tiles narrower than 128 only pay when they fill an otherwise idle machine.

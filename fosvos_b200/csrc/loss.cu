@@ -19,48 +19,123 @@ __device__ __forceinline__ void loss_elem(float x, float lab, LossAcc& a) {
   a.s_neg += -((1.f - y) * lv);                            // loss_neg                      :37
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int LOSS_THREADS = 1024;              // the exp/log chains need the occupancy ...
+constexpr int LOSS_MAX_BLOCKS = 160;            // ... but every block ends with a same-address counter atomic (~27 cycles each,
+                                                // serialised): ONE fat block per SM; per-block partial sums live behind stats[8]
+
+// Block reduction of the three sums into this block's slot; the last block to finish (one counter atomic per
+// block, not three same-address double atomics) adds the slots up in a fixed order and finalises.
+__device__ __forceinline__ void loss_finish(LossAcc a, double* __restrict__ stats, float* __restrict__ loss, long long n,
+                                            int size_average, bool counts_given) {
+  double pos = warp_sum((double)a.pos), sp = warp_sum((double)a.s_pos), sn = warp_sum((double)a.s_neg);
+  __shared__ double sm[3][LOSS_THREADS / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][wid] = pos; sm[1][wid] = sp; sm[2][wid] = sn; }
+  __syncthreads();
+  if (wid == 0) {
+    pos = lane < LOSS_THREADS / 32 ? sm[0][lane] : 0.0;
+    sp = lane < LOSS_THREADS / 32 ? sm[1][lane] : 0.0;
+    sn = lane < LOSS_THREADS / 32 ? sm[2][lane] : 0.0;
+    pos = warp_sum(pos); sp = warp_sum(sp); sn = warp_sum(sn);
+    if (lane == 0) {
+      double* slot = stats + 8 + 3 * blockIdx.x;
+      slot[0] = pos; slot[1] = sp; slot[2] = sn;
+      __threadfence();
+      unsigned long long* counter = reinterpret_cast<unsigned long long*>(&stats[4]);
+      last = atomicAdd(counter, 1ULL) + 1ULL == gridDim.x;
+    }
+  }
+  __syncthreads();
+  if (last) {
+    // every slot in ONE round trip (a serial loop of L2 reads would cost microseconds), then a fixed-order sum
+    __shared__ double part[3 * LOSS_MAX_BLOCKS];
+    __threadfence();
+    const int nslots = 3 * (int)gridDim.x;
+    for (int t = threadIdx.x; t < nslots; t += LOSS_THREADS) part[t] = __ldcg(stats + 8 + t);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double P = 0.0, SP = 0.0, SN = 0.0;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) { P += part[3 * b]; SP += part[3 * b + 1]; SN += part[3 * b + 2]; }
+      P = warp_sum(P); SP = warp_sum(SP); SN = warp_sum(SN);
+      if (threadIdx.x == 0) {
+        if (counts_given) P = stats[0];
+        const double Nn = (double)n - P, tot = (double)n;
+        stats[0] = P;
+        stats[1] = Nn;
+        stats[2] = SP;
+        stats[3] = SN;
+        // fp32 like the reference: num_labels_neg / num_total * loss_pos + num_labels_pos / num_total * loss_neg  :39
+        float v = (float)Nn / (float)tot * (float)SP + (float)P / (float)tot * (float)SN;
+        if (size_average) v = v / (float)n;                                                          // :41-42
+        *loss = v;
+        *reinterpret_cast<unsigned long long*>(&stats[4]) = 0ULL;   // ready for the next launch (no memset node needed)
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS)
 bal_loss_fwd_kernel(const float* __restrict__ out, const float* __restrict__ lab, long long n, int size_average,
                     double* __restrict__ stats, float* __restrict__ loss) {
   LossAcc a{0.f, 0.f, 0.f};
   const long long n4 = n / 4;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  for (long long i = tid; i < n4; i += nth) {
+  long long i = tid;
+  for (; i + nth < n4; i += 2 * nth) {           // two independent 16-byte loads per stream in flight
+    const float4 x0 = reinterpret_cast<const float4*>(out)[i], x1 = reinterpret_cast<const float4*>(out)[i + nth];
+    const float4 l0 = reinterpret_cast<const float4*>(lab)[i], l1 = reinterpret_cast<const float4*>(lab)[i + nth];
+    loss_elem(x0.x, l0.x, a); loss_elem(x0.y, l0.y, a); loss_elem(x0.z, l0.z, a); loss_elem(x0.w, l0.w, a);
+    loss_elem(x1.x, l1.x, a); loss_elem(x1.y, l1.y, a); loss_elem(x1.z, l1.z, a); loss_elem(x1.w, l1.w, a);
+  }
+  for (; i < n4; i += nth) {
     const float4 x = reinterpret_cast<const float4*>(out)[i];
     const float4 l = reinterpret_cast<const float4*>(lab)[i];
     loss_elem(x.x, l.x, a); loss_elem(x.y, l.y, a); loss_elem(x.z, l.z, a); loss_elem(x.w, l.w, a);
   }
-  for (long long i = n4 * 4 + tid; i < n; i += nth) loss_elem(out[i], lab[i], a);
+  for (long long j = n4 * 4 + tid; j < n; j += nth) loss_elem(out[j], lab[j], a);
+  loss_finish(a, stats, loss, n, size_average, false);
+}
 
-  double pos = warp_sum((double)a.pos), sp = warp_sum((double)a.s_pos), sn = warp_sum((double)a.s_neg);
-  __shared__ double sm[3][8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { sm[0][wid] = pos; sm[1][wid] = sp; sm[2][wid] = sn; }
-  __syncthreads();
-  if (wid == 0) {
-    pos = lane < 8 ? sm[0][lane] : 0.0;
-    sp = lane < 8 ? sm[1][lane] : 0.0;
-    sn = lane < 8 ? sm[2][lane] : 0.0;
-    pos = warp_sum(pos); sp = warp_sum(sp); sn = warp_sum(sn);
-    if (lane == 0) {
-      atomicAdd(&stats[0], pos);
-      atomicAdd(&stats[2], sp);
-      atomicAdd(&stats[3], sn);
-      __threadfence();
-      unsigned long long* counter = reinterpret_cast<unsigned long long*>(&stats[4]);
-      const unsigned long long done = atomicAdd(counter, 1ULL) + 1ULL;
-      if (done == gridDim.x) {                  // last block: finalise
-        __threadfence();
-        const double P = atomicAdd(&stats[0], 0.0), SP = atomicAdd(&stats[2], 0.0), SN = atomicAdd(&stats[3], 0.0);
-        const double Nn = (double)n - P, tot = (double)n;
-        stats[1] = Nn;
-        // fp32 like the reference: num_labels_neg / num_total * loss_pos + num_labels_pos / num_total * loss_neg  :39
-        float v = (float)Nn / (float)tot * (float)SP + (float)P / (float)tot * (float)SN;
-        if (size_average) v = v / (float)n;                                                          // :41-42
-        *loss = v;
-      }
-    }
+// Forward AND backward in one pass (12 B/pixel instead of 20) when the label counts are known up front --
+// they depend on the label only, which one-shot fine-tuning keeps for hundreds of iterations:
+// stats[0] = number of positive labels on entry (from a previous forward on the same label).
+__global__ void __launch_bounds__(LOSS_THREADS)
+bal_loss_fused_kernel(const float* __restrict__ out, const float* __restrict__ lab, long long n, int size_average,
+                      double* __restrict__ stats, float* __restrict__ loss, const float* __restrict__ grad_out, float grad_scale,
+                      float* __restrict__ dx) {
+  const float tot = (float)n;
+  float g = grad_scale * (grad_out ? *grad_out : 1.f);
+  if (size_average) g /= tot;
+  const double P = stats[0];
+  const float w1 = (float)((double)n - P) / tot * g;   // y = 1: neg/total
+  const float w0 = (float)P / tot * g;                 // y = 0: pos/total
+  LossAcc a{0.f, 0.f, 0.f};
+  // One exponential serves both: t = exp(-|x|) = exp(x - 2 x [x >= 0]) (osvos_layers.py:33), loss term
+  // x (y - z) - log(1 + t), sigmoid = 1 / (1 + t) or t / (1 + t).  MUFU-based exp / log / reciprocal (relative error
+  // ~1e-6, far inside the 2e-5 / 1e-4 parity bounds of loss and gradient) keep this pass HBM-bound.
+  auto f = [&](float x, float l) -> float {
+    const float y = l >= 0.5f ? 1.f : 0.f;
+    const float z = x >= 0.f ? 1.f : 0.f;
+    const float t = __expf(-fabsf(x));
+    const float u = 1.f + t;
+    const float lv = x * (y - z) - __logf(u);
+    a.pos += y;
+    a.s_pos += -(y * lv);
+    a.s_neg += -((1.f - y) * lv);
+    const float r = __frcp_rn(u);
+    const float sg = x >= 0.f ? r : t * r;
+    return l >= 0.5f ? w1 * (sg - 1.f) : w0 * sg;
+  };
+  const long long n4 = n / 4;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 x = reinterpret_cast<const float4*>(out)[i];
+    const float4 l = reinterpret_cast<const float4*>(lab)[i];
+    reinterpret_cast<float4*>(dx)[i] = make_float4(f(x.x, l.x), f(x.y, l.y), f(x.z, l.z), f(x.w, l.w));
   }
+  for (long long j = n4 * 4 + tid; j < n; j += nth) dx[j] = f(out[j], lab[j]);
+  loss_finish(a, stats, loss, n, size_average, true);
 }
 
 __global__ void __launch_bounds__(256)
@@ -135,14 +210,27 @@ using namespace fosvos;
 
 extern "C" {
 
+size_t fosvos_bal_loss_stats_bytes(void) { return sizeof(double) * (8 + 3 * LOSS_MAX_BLOCKS); }
+
+static int loss_blocks(long long numel) { return (int)min((long long)min(num_sms(), LOSS_MAX_BLOCKS), ceil_div_ll(numel, 4 * LOSS_THREADS)); }
+
 int fosvos_bal_loss_fwd(const float* output, const float* label, long long numel, int size_average, double* stats,
                         float* loss, fosvos_stream_t stream) {
   FOSVOS_REQUIRE(output && label && stats && loss && numel > 0, "bal_loss_fwd: bad arguments");
   FOSVOS_REQUIRE(((uintptr_t)output & 15) == 0 && ((uintptr_t)label & 15) == 0, "bal_loss_fwd: pointers must be 16-byte aligned");
   cudaMemsetAsync(stats, 0, 8 * sizeof(double), as_stream(stream));
-  const int blocks = (int)min((long long)num_sms() * 4, ceil_div_ll(numel, 1024));
-  bal_loss_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, loss);
+  bal_loss_fwd_kernel<<<loss_blocks(numel), LOSS_THREADS, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, loss);
   return check_launch("bal_loss_fwd");
+}
+
+int fosvos_bal_loss_fwd_bwd(const float* output, const float* label, long long numel, int size_average, double* stats,
+                            float* loss, const float* grad_out, float grad_scale, float* dx, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(output && label && stats && loss && dx && numel > 0, "bal_loss_fwd_bwd: bad arguments");
+  FOSVOS_REQUIRE(((uintptr_t)output & 15) == 0 && ((uintptr_t)label & 15) == 0 && ((uintptr_t)dx & 15) == 0,
+                 "bal_loss_fwd_bwd: pointers must be 16-byte aligned");
+  bal_loss_fused_kernel<<<loss_blocks(numel), LOSS_THREADS, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, loss,
+                                                                                   grad_out, grad_scale, dx);
+  return check_launch("bal_loss_fwd_bwd");
 }
 
 int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel, int size_average,

@@ -41,7 +41,7 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, i
 // Gradient goes to the FIRST maximum of the window in (row, col) scan order -- the index
 // max_pool2d_with_indices records (strict '>' comparison against a running maximum).
 template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int H,
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* add, T* dx, int H,
                                    int W, int C, int OH, int OW, long long total) {
   const int groups = C / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -75,6 +75,12 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = arg[j] == k ? gsrc[j] : 0.f;
+        if (add) {                                    // gradient fan-in: the other consumer's contribution (may alias dx)
+          float a[8];
+          load8(add + ((n * H + iy) * W + ix) * C + g * 8, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
         store8(dx + ((n * H + iy) * W + ix) * C + g * 8, o);
       }
     }
@@ -100,12 +106,17 @@ int fosvos_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, in
 
 int fosvos_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
                           fosvos_stream_t stream) {
+  return fosvos_maxpool2x2_bwd_add(x, dy, nullptr, dx, N, H, W, C, dtype, stream);
+}
+
+int fosvos_maxpool2x2_bwd_add(const void* x, const void* dy, const void* add, void* dx, int N, int H, int W, int C, int dtype,
+                              fosvos_stream_t stream) {
   FOSVOS_REQUIRE(x && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool2x2_bwd: bad shape (C=%d must be a multiple of 8)", C);
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   const long long total = (long long)N * OH * OW * (C / 8);
   const int blocks = (int)min((long long)num_sms() * 16, ceil_div_ll(total, 256));
   FOSVOS_DISPATCH_DTYPE(dtype, T, {
-    maxpool_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)dy, (T*)dx, H, W, C, OH, OW, total);
+    maxpool_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)dy, (const T*)add, (T*)dx, H, W, C, OH, OW, total);
   });
   return check_launch("maxpool2x2_bwd");
 }

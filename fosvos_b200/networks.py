@@ -322,12 +322,42 @@ class OSVOS_VGG(nn.Module):
         first = [0]
         for c in convs[:-1]:
             first.append(first[-1] + len(c))
+        # The side_prep branch of every stage output only needs dsp: its data gradient (masked by the stage output's
+        # ReLU) is issued one stage ahead, off the main chain; the pool gradient coming down the backbone is then
+        # added INTO it (fan-in in the pool kernel, a coalesced elementwise read).
+        dA_side: List[Optional[torch.Tensor]] = [None] * 5
+        side_done: List[Optional[torch.cuda.Event]] = [None] * 5
+
+        def side_branch(si: int, on_aux: bool) -> None:
+            a_out = saved["stage_out"][si]
+            pc = self._packed_for(self.side_prep[si - 1], need_dgrad=True)
+            dA_side[si] = torch.empty_like(a_out)
+            if aux is None or not on_aux:
+                ops.conv3x3(dsp[si - 1], pc.w_dgrad, None, a_out.shape[3], L.CONV_MASK, mask=a_out, out=dA_side[si], impl=impl)
+            else:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                aux.wait_event(ev)
+                with torch.cuda.stream(aux):
+                    ops.conv3x3(dsp[si - 1], pc.w_dgrad, None, a_out.shape[3], L.CONV_MASK, mask=a_out, out=dA_side[si], impl=impl)
+                    side_done[si] = torch.cuda.Event()
+                    side_done[si].record(aux)
+            wgrad(f"side_prep.{si - 1}", a_out, dsp[si - 1])
+
+        fanin_pool = os.environ.get("FOSVOS_BWD_FANIN", "epilogue") == "pool"
+        if fanin_pool:
+            side_branch(4, on_aux=False)
         dA: Optional[torch.Tensor] = None          # gradient w.r.t. the current stage's output (pre-activation-masked)
         for si in range(4, -1, -1):
-            a_out = saved["stage_out"][si]
-            if si > 0:
-                spc = self.side_prep[si - 1]
-                pc = self._packed_for(spc, need_dgrad=True)
+            if fanin_pool:
+                if si == 4:
+                    dA = dA_side[4]
+                if si - 1 > 0:
+                    side_branch(si - 1, on_aux=True)       # needed by the pool gradient at the END of this stage
+            elif si > 0:
+                # fan-in in the conv epilogue: dA (+)= mask * convT(dsp) on the main chain
+                a_out = saved["stage_out"][si]
+                pc = self._packed_for(self.side_prep[si - 1], need_dgrad=True)
                 wgrad(f"side_prep.{si - 1}", a_out, dsp[si - 1])
                 flags = L.CONV_MASK | (L.CONV_ACCUMULATE if dA is not None else 0)
                 dA = ops.conv3x3(dsp[si - 1], pc.w_dgrad, None, a_out.shape[3], flags, mask=a_out, out=dA, impl=impl)
@@ -346,7 +376,9 @@ class OSVOS_VGG(nn.Module):
                 # dX masked by (x_in > 0): x_in is the previous layer's post-ReLU output (or its pooled copy)
                 dz = ops.conv3x3(dz, pc.w_dgrad, None, x_in.shape[3], L.CONV_MASK, mask=x_in, impl=impl)
             if si > 0:
-                dA = ops.maxpool2x2_bwd(saved["pool_in"][si - 1], dz)
+                if si - 1 > 0 and side_done[si - 1] is not None:
+                    main.wait_event(side_done[si - 1])
+                dA = ops.maxpool2x2_bwd(saved["pool_in"][si - 1], dz, add=dA_side[si - 1])
         if aux is not None:
             main.wait_stream(aux)
         keep.clear()

@@ -148,6 +148,9 @@ class OnlineTrainer:
                     cout, cin = params[name].shape[0], params[name].shape[1]
                     self.wgrad_ws[name[:-len(".weight")]] = ops.wgrad_workspace(ops.pad8(cin), ops.pad8(cout), dev)
         self._fold_table = None
+        # label counts of the resident mask: they only change with set_frame(), so loss and gradient are ONE pass
+        self.loss_stats = torch.zeros(L.lib().fosvos_bal_loss_stats_bytes() // 8, dtype=torch.float64, device=dev)
+        ops.bal_loss_fwd(self.mask, self.mask, False, stats=self.loss_stats)
         self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
         self.last_loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.counter = 0
@@ -161,13 +164,11 @@ class OnlineTrainer:
         net = self.net
         outs, _, _, saved = net._run_forward(self.frame, save=True)
         douts: List[Optional[torch.Tensor]] = [None] * 5
-        loss, stats = ops.bal_loss_fwd(outs[4], self.mask, False)
-        douts[4] = ops.bal_loss_bwd(outs[4], self.mask, False, stats, None, self.scale)
+        loss, douts[4] = ops.bal_loss_fwd_bwd(outs[4], self.mask, False, self.loss_stats, None, self.scale)
         total = loss
         if self.deep_w is not None:
             for i in range(4):
-                li, st = ops.bal_loss_fwd(outs[i], self.mask, False)
-                douts[i] = ops.bal_loss_bwd(outs[i], self.mask, False, st, self.deep_w, self.scale)
+                li, douts[i] = ops.bal_loss_fwd_bwd(outs[i], self.mask, False, self.loss_stats, self.deep_w, self.scale)
                 total = total + self.deep_w * li
         self.last_loss.copy_(total)
         self.loss_sum.add_(total)
@@ -214,8 +215,14 @@ class OnlineTrainer:
             _repack_in_place(self.net)              # builds the multi-tensor repack table (host -> device copies)
         torch.cuda.current_stream().wait_stream(s)
         self._micro_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._micro_graph):
+        # captured on a high-priority stream: the dependency chain (forward, data gradients) wins the SMs over the
+        # weight gradients / side branches that the network issues on its default-priority auxiliary stream
+        import os
+        hp = torch.cuda.Stream(priority=-1 if os.environ.get("FOSVOS_HP", "1") != "0" else 0)
+        hp.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(self._micro_graph, stream=hp):
             self._micro()
+        torch.cuda.current_stream().wait_stream(hp)
         c0 = L.CALLS[0]
         self._step_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._step_graph, pool=self._micro_graph.pool()):
@@ -252,6 +259,7 @@ class OnlineTrainer:
         (host tensors are uploaded; pinned ones asynchronously)."""
         self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)
         self.mask.copy_(mask.reshape(self.mask.shape), non_blocking=True)
+        ops.bal_loss_fwd(self.mask, self.mask, False, stats=self.loss_stats)      # label counts of the new mask
 
     def run(self, n_iters: int, losses_out: Optional[list] = None) -> torch.Tensor:
         if self.use_graph and self._micro_graph is None:

@@ -149,12 +149,17 @@ def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def maxpool2x2_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+def maxpool2x2_bwd(x: torch.Tensor, dy: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradient of the pool w.r.t. its input; with ``add`` (same shape as x) the result is written INTO it:
+    add += pool gradient (the fan-in of the stage output's two consumers)."""
     L.require_device(x.device)
     n, h, w, c = x.shape
     assert dy.shape == (n, (h + 1) // 2, (w + 1) // 2, c) and dy.dtype == x.dtype
-    dx = torch.empty_like(x)
-    L.check(L.lib().fosvos_maxpool2x2_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, c, L.dtype_code(x.dtype), L.stream()), "maxpool2x2_bwd")
+    if add is not None:
+        assert add.shape == x.shape and add.dtype == x.dtype and add.is_contiguous()
+    dx = torch.empty_like(x) if add is None else add
+    L.check(L.lib().fosvos_maxpool2x2_bwd_add(x.data_ptr(), dy.data_ptr(), L.ptr(add), dx.data_ptr(), n, h, w, c,
+                                              L.dtype_code(x.dtype), L.stream()), "maxpool2x2_bwd")
     return dx
 
 
@@ -228,16 +233,34 @@ def side_bwd(sp: Sequence[torch.Tensor], params: torch.Tensor, dout: Sequence[Op
 
 
 # ---- loss -----------------------------------------------------------------------------------
-def bal_loss_fwd(output: torch.Tensor, label: torch.Tensor, size_average: bool) -> Tuple[torch.Tensor, torch.Tensor]:
-    """-> (loss 0-dim fp32, stats (8,) float64)"""
+def bal_loss_fwd(output: torch.Tensor, label: torch.Tensor, size_average: bool,
+                 stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (loss 0-dim fp32, stats float64: [0] positives, [1] negatives, [2] sum loss_pos, [3] sum loss_neg, ...)"""
     L.require_device(output.device)
     assert output.dtype == torch.float32 and label.dtype == torch.float32 and output.numel() == label.numel()
     output, label = output.contiguous(), label.contiguous()
-    stats = torch.empty(8, dtype=torch.float64, device=output.device)
+    if stats is None:
+        stats = torch.empty(L.lib().fosvos_bal_loss_stats_bytes() // 8, dtype=torch.float64, device=output.device)
+    assert stats.dtype == torch.float64 and stats.numel() * 8 >= L.lib().fosvos_bal_loss_stats_bytes()
     loss = torch.empty((), dtype=torch.float32, device=output.device)
     L.check(L.lib().fosvos_bal_loss_fwd(output.data_ptr(), label.data_ptr(), output.numel(), int(size_average),
                                         stats.data_ptr(), loss.data_ptr(), L.stream()), "bal_loss_fwd")
     return loss, stats
+
+
+def bal_loss_fwd_bwd(output: torch.Tensor, label: torch.Tensor, size_average: bool, stats: torch.Tensor,
+                     grad_out: Optional[torch.Tensor] = None, grad_scale: float = 1.0, out: Optional[torch.Tensor] = None):
+    """Loss and its gradient in one pass; ``stats`` from an earlier ``bal_loss_fwd`` on the SAME label (its counts are
+    reused, its sums are overwritten).  -> (loss 0-dim fp32, dx)"""
+    L.require_device(output.device)
+    assert output.dtype == torch.float32 and label.dtype == torch.float32 and output.numel() == label.numel()
+    output, label = output.contiguous(), label.contiguous()
+    dx = torch.empty_like(output) if out is None else out
+    loss = torch.empty((), dtype=torch.float32, device=output.device)
+    L.check(L.lib().fosvos_bal_loss_fwd_bwd(output.data_ptr(), label.data_ptr(), output.numel(), int(size_average), stats.data_ptr(),
+                                            loss.data_ptr(), L.ptr(grad_out), float(grad_scale), dx.data_ptr(), L.stream()),
+            "bal_loss_fwd_bwd")
+    return loss, dx
 
 
 def bal_loss_bwd(output: torch.Tensor, label: torch.Tensor, size_average: bool, stats: torch.Tensor,

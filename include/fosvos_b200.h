@@ -150,6 +150,9 @@ int fosvos_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, in
  * elsewhere (what autograd's max_pool2d_with_indices backward does). */
 int fosvos_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C,
                           int dtype, fosvos_stream_t stream);
+/* Same with gradient fan-in: dx = add + pool gradient (add: same shape as dx, may alias it, may be NULL). */
+int fosvos_maxpool2x2_bwd_add(const void* x, const void* dy, const void* add, void* dx, int N, int H,
+                              int W, int C, int dtype, fosvos_stream_t stream);
 
 /* ---- side-output chain (osvos_vgg.py:69-82) -------------------------------------------
  * score_dsn 1x1 (:75) -> upscale_ ConvT (:76) -> crop (:77) for the four side maps, and
@@ -201,8 +204,17 @@ int fosvos_side_check_diagonal(const float* const* upscale_w, int* violations_de
  * loss (device fp32 scalar) = neg/total*stats[2] + pos/total*stats[3], / numel if size_average.
  * fwd zeroes and fills stats; bwd reads it:  dx = g * w(y) * (sigmoid(x) - y) [/ numel],
  * g = *grad_out (device fp32 scalar, NULL -> 1) times grad_scale. */
+/* `stats`: fosvos_bal_loss_stats_bytes() bytes of doubles: [0] positives, [1] negatives, [2] sum loss_pos,
+ * [3] sum loss_neg, [4] block counter (left at 0), [8..] per-block partial sums. */
+size_t fosvos_bal_loss_stats_bytes(void);
 int fosvos_bal_loss_fwd(const float* output, const float* label, long long numel, int size_average,
                         double* stats, float* loss, fosvos_stream_t stream);
+/* Forward and backward in ONE pass over output/label (12 B/pixel): needs the label counts up front --
+ * `stats` comes from an earlier fosvos_bal_loss_fwd on the SAME label (one-shot fine-tuning keeps the label for
+ * hundreds of iterations, train_online.py:77-81).  dx = grad_scale * (*grad_out or 1) * d loss / d output. */
+int fosvos_bal_loss_fwd_bwd(const float* output, const float* label, long long numel, int size_average,
+                            double* stats, float* loss, const float* grad_out, float grad_scale,
+                            float* dx, fosvos_stream_t stream);
 int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel, int size_average,
                         const double* stats, const float* grad_out, float grad_scale, float* dx,
                         fosvos_stream_t stream);

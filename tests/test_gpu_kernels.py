@@ -412,6 +412,24 @@ def test_balanced_loss(shape, size_average):
     assert torch.allclose(dx.cpu(), gref, rtol=1e-4, atol=1e-7 * float(gref.abs().max()) + 1e-12)
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 4, 4), (2, 1, 37, 53), (1, 1, 480, 854)])
+@pytest.mark.parametrize("size_average", [True, False])
+def test_balanced_loss_fused_forward_backward(shape, size_average):
+    """One-pass loss + gradient with the label counts of an earlier forward == the two-kernel path."""
+    g = _gen(61)
+    x = torch.randn(shape, generator=g) * 3
+    lab = (torch.rand(shape, generator=g) > 0.7).float()
+    xr = x.clone().requires_grad_(True)
+    ref = O.class_balanced_cross_entropy_loss(xr, lab, size_average=size_average)
+    (0.2 * ref).backward()
+    xd, ld = x.to(DEV), lab.to(DEV)
+    _, stats = ops.bal_loss_fwd(torch.zeros_like(xd), ld, size_average)      # counts only depend on the label
+    for _ in range(2):                                                       # the stats buffer is reusable
+        loss, dx = ops.bal_loss_fwd_bwd(xd, ld, size_average, stats, None, 0.2)
+        assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref)) + 1e-7
+        assert torch.allclose(dx.cpu(), xr.grad, rtol=1e-4, atol=1e-7 * float(xr.grad.abs().max()) + 1e-12)
+
+
 def test_balanced_loss_golden_kat():
     from fosvos_b200 import class_balanced_cross_entropy_loss
     from conftest import GOLDEN

@@ -55,7 +55,7 @@ for (h, w, cin, cout) in LAYERS:
     y = torch.empty((batch, h, w, cout), device=dev, dtype=torch.bfloat16)
     flops = 2.0 * batch * h * w * cin * cout * 9
     row = []
-    for bn in ([None] if cout <= 16 else [None, 64, 128, 256]):
+    for bn in ([None] if (cout <= 16 or os.environ.get("PROBE_BN", "1") != "1") else [None, 64, 128, 256]):
         if bn is not None and bn > max(cout, 64):
             continue
         if bn is None:
@@ -68,4 +68,15 @@ for (h, w, cin, cout) in LAYERS:
             t = timeit(lambda: ops.conv3x3(x, wp, bias, cout, L.CONV_BIAS | L.CONV_RELU | d, out=y))
             row.append(f"{'bn' + str(bn) + ':' if bn else ''}{name}={t:.1f}" + (f"({flops / t / 1e6:.0f}TF)" if name == "full" else ""))
     os.environ.pop("FOSVOS_TC_BN", None)
+    if cout >= 64 and os.environ.get("PROBE_MASK", "1") == "1":
+        # data-gradient epilogue: ReLU mask of the layer input, staged-slab path vs register path
+        mk = (torch.rand((batch, h, w, cout), device=dev) > 0.5).to(torch.bfloat16)
+        for name, env in (("mask_slab", None), ("mask_regs", "1")):
+            if env is None:
+                os.environ.pop("FOSVOS_TC_MASK_REGS", None)
+            else:
+                os.environ["FOSVOS_TC_MASK_REGS"] = env
+            t = timeit(lambda: ops.conv3x3(x, wp, None, cout, L.CONV_MASK, mask=mk, out=y))
+            row.append(f"{name}={t:.1f}")
+        os.environ.pop("FOSVOS_TC_MASK_REGS", None)
     print(f"{h}x{w} {cin}->{cout}: " + " ".join(row), flush=True)

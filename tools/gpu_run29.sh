@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 420 python -m pytest tests -q -m gpu --timeout 120 -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|^E  +(Assert|assert|Runtime|Type|Attr|Value|Key|Index|Name)|^FAILED" gpurun_out/t_all.log | cut -c1-300 | head -30
+timeout 600 python bench.py --iters 200 --steps 1 --warmup 2 > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_tmp.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_tmp.json'))
+print({k:d[k] for k in ('value','ms_per_step','inference_fps','finetune_s_per_sequence','finetune_tflops')}, d['e2e']['value'], d['roofline']['frac'], d['roofline_side_chain']['frac'], d['roofline_loss'])
+PY
+timeout 100 python tools/side_probe.py 8 2>&1 | tail -3

@@ -62,3 +62,5 @@ print(f"bal_loss_fwd batch {batch}: {t:.1f} us  {8 * x.numel() / t / 1e3:.0f} GB
 dx = torch.empty_like(x)
 t = timeit(lambda: ops.bal_loss_bwd(x, lab, False, stats, None, 1.0, out=dx))
 print(f"bal_loss_bwd batch {batch}: {t:.1f} us  {12 * x.numel() / t / 1e3:.0f} GB/s")
+t = timeit(lambda: ops.bal_loss_fwd_bwd(x, lab, False, stats, None, 1.0, out=dx))
+print(f"bal_loss_fwd_bwd (one pass) batch {batch}: {t:.1f} us  {12 * x.numel() / t / 1e3:.0f} GB/s")
