@@ -297,3 +297,45 @@ def test_full_size_480x854_against_oracle(precision):
     # batch > 1 gives the same per-frame result
     outs2, _, mask2 = net.predict(torch.cat([x, x.flip(3)]).to(DEV))
     assert torch.equal(mask2[0].cpu(), mask[0].cpu())
+
+
+def test_config2_pruned_batch_480x854_bf16():
+    """BASELINE configs[2]: channel-pruned VGG (50 % of the filters of every stage conv, bias-free convs as
+    prune.py:490-514 builds them), batched bf16 inference at 480x854, against the oracle on the pruned state_dict."""
+    from fosvos_b200 import prune as P
+    xs, ms = synth.make_frame(0, 0, 120, 214)
+    sd = synth.calibrate(synth.make_state_dict(0, "structured"), O.vgg_forward, xs, mask=ms)
+    net = _net(sd, "bf16")
+    P.l2_prune_half(net, 0.5)
+    psd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    assert psd["stages.4.5.weight"].shape == (256, 256, 3, 3) and "stages.0.0.bias" not in psd
+    frames = torch.cat([synth.make_frame(0, f, 480, 854)[0] for f in range(3)])
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        ref = O.vgg_forward(psd, frames)
+    outs, prob, mask = net.predict(frames.to(DEV))
+    err = float((prob.cpu() - O.probabilities(ref[4])).abs().max())
+    assert err <= 3e-2, err          # pruning removes the calibration margin: logits sit closer to 0 than in the dense net
+    ref_mask = O.binarise(O.probabilities(ref[4]))
+    for f in range(3):
+        assert _iou(mask[f].cpu(), ref_mask[f]) >= 0.995
+
+
+@pytest.mark.parametrize("hw", [(240, 427), (384, 683)])
+def test_finetune_at_augmented_frame_sizes(hw):
+    """train-time Resize scales {0.5, 0.8} of 480x854 (custom_transforms.py:63-109): the fine-tune step at the other
+    frame sizes the online loop sees, fp32, two iterations + one optimizer step against the oracle."""
+    H, W = hw
+    x, m = synth.make_frame(1, 0, H, W)
+    xs, ms = synth.make_frame(0, 0, 120, 214)
+    sd = synth.calibrate(synth.make_state_dict(0, "structured"), O.vgg_forward, xs, mask=ms)
+    torch.set_num_threads(os.cpu_count())
+    ref_sd, ref_losses = O.finetune(sd, x, m, 2, 2)
+    net = _net(sd, "fp32")
+    losses = []
+    FB.finetune(net, x.to(DEV), m.to(DEV), 2, 2, use_graph=True, losses_out=losses)
+    assert np.allclose(losses, ref_losses, rtol=2e-4), (losses, ref_losses)
+    mine = net.state_dict()
+    for k in ["stages.0.0.weight", "stages.2.3.weight", "stages.4.5.bias", "side_prep.3.weight", "fuse.weight"]:
+        d, dr = mine[k].cpu() - sd[k], ref_sd[k] - sd[k]
+        assert float((d - dr).abs().max()) <= 5e-3 * float(dr.abs().max()) + 1e-12, k
