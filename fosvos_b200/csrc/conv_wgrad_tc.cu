@@ -18,6 +18,12 @@
 // [tap][M][N] workspace; `wgrad_unpack_kernel` then adds it into the OIHW fp32 .grad tensor.  The
 // workspace may stay live across micro-iterations (`_accumulate` / `_finish`), so the unpack runs once
 // per optimizer step.
+// First layer (Cin padded to 8, `c8`): a pixel of X is 16 bytes = one row of an UN-swizzled MN-major core matrix, and
+// the frame is described to TMA as (8 W, H, N), so ONE 160 B x 18-row halo box per 16 x 8 patch serves all nine
+// taps: tap (r, s) is the same tile read from byte offset r * 160 + s * 16.  With SBO = 16 (next tap along N) and
+// LBO = 160 (next image row = next 8 pixels along K) one MMA covers the three taps of a kernel row (N = 32, the
+// fourth block is ignored), so a patch is visited once (not once per kernel column) and dZ is read once.
+//
 // Bias gradient db[co] = sum_p dZ[p][co]: the dZ boxes are in shared memory anyway, so the four epilogue
 // warps, otherwise idle until the accumulators are complete, sum them on the side; the CTAs that see the
 // same dZ tile (three kernel columns x the tiles of the X-channel dimension) take every share-th patch each.
@@ -47,6 +53,8 @@ struct WgParams {
   int x_is_a;
   int stages, stage_bytes, a_bytes;
   int x_block;               // bytes of one shifted 64-channel box: (TH+2)*TW*128
+  int c8;                    // first-layer mode (see the header comment)
+  int c8_lbo, c8_sbo;        // descriptor strides of its un-swizzled X operand (160 / 16)
   int debug;                 // FOSVOS_WG_DEBUG: 1 = skip the reductions (timing experiments only), 2 = no start rotation
 };
 
@@ -59,6 +67,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+
+constexpr int WG_C8_ROW = 160, WG_C8_BOX = 18 * WG_C8_ROW, WG_C8_BYTES = 3072;
+
+// Un-swizzled MN-major operand: 16 contiguous bytes along MN, 8 K rows 16 bytes apart form a core matrix;
+// `sbo` = byte distance between core matrices along MN, `lbo` = along K.
+__device__ __forceinline__ uint64_t umma_desc_noswizzle_mnmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 
@@ -79,14 +100,15 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   // work item
   int item = blockIdx.x;
   const int split = item % p.splits; item /= p.splits;
-  const int s = item % 3; item /= 3;
+  const int s = p.c8 ? 0 : item % 3;
+  if (!p.c8) item /= 3;
   const int nt = item % p.n_tiles;
   const int mt = item / p.n_tiles;
   // Bias gradient: the CTAs (s, other-dimension tile) that share this CTA's dZ tile split its patches between them
   // (patch pt belongs to CTA pt % share == share_id), so the extra shared-memory reads are spread evenly instead of
   // slowing one CTA in three -- the MMA stream already uses the full shared-memory bandwidth.
   const bool do_bias = p.db != nullptr;
-  const int share = 3 * (p.x_is_a ? p.m_tiles : p.n_tiles);
+  const int share = (p.c8 ? 1 : 3) * (p.x_is_a ? p.m_tiles : p.n_tiles);
   const int share_id = s * (p.x_is_a ? p.m_tiles : p.n_tiles) + (p.x_is_a ? mt : nt);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform roles
@@ -101,6 +123,13 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     ptx::fence_barrier_init();
   }
   if (threadIdx.x < 128) bias_red[threadIdx.x] = 0.f;
+  if (p.c8) {
+    // tails of the X stages: never written by TMA, read (and ignored) by the fourth column block of the last kernel row
+    const int per = (WG_C8_BYTES - WG_C8_BOX) / 16;
+    for (int i = threadIdx.x; i < p.stages * per; i += WG_THREADS)
+      *reinterpret_cast<uint4*>(smem + (i / per) * p.stage_bytes + p.a_bytes + WG_C8_BOX + (i % per) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+  }
   if (warp == 1) ptx::tmem_alloc(tmem_ptr, 512);
   ptx::tc_fence_before();
   __syncthreads();
@@ -130,7 +159,14 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int x0 = tx * TW, y0 = ty * TH;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * p.stage_bytes;
-        if (ptx::elect_one()) {
+        if (p.c8) {
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full_bar[stage], WG_C8_BOX + nb_z * WG_PLAIN_BLOCK);
+            ptx::tma_load_3d_a(ptx::smem_u32(st + x_off), &map_x, ptx::smem_u32(&full_bar[stage]), (x0 - 1) * 8, y0 - 1, n);
+            for (int j = 0; j < nb_z; ++j)
+              ptx::tma_load_4d(st + z_off + j * WG_PLAIN_BLOCK, &map_z, &full_bar[stage], zc0 + 64 * j, x0, y0, n);
+          }
+        } else if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
           for (int j = 0; j < nb_x; ++j)
             ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], xc0 + 64 * j, x0 + s - 1, y0 - 1, n);
@@ -156,7 +192,22 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         ptx::tc_fence_after();
         const uint32_t st = ptx::smem_u32(smem + stage * p.stage_bytes);
         const uint32_t a_base = st, b_base = st + p.a_bytes;
-        if (ptx::elect_one()) {
+        if (p.c8) {
+          if (ptx::elect_one()) {
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t da = umma_desc_sw128_mnmajor(a_base + kk * 2048, WG_PLAIN_BLOCK);
+                // 16 pixels = image rows 2 kk, 2 kk + 1 of the patch, seen through kernel row r
+                const uint64_t db = umma_desc_noswizzle_mnmajor(b_base + (r + 2 * kk) * WG_C8_ROW, p.c8_lbo, p.c8_sbo);
+                ptx::umma_bf16(tmem_base + r * p.n_cols, da, db, idesc, (pt != p_begin) || (kk != 0));
+              }
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (pt == p_end - 1) ptx::umma_commit(done_bar);
+          }
+        } else if (ptx::elect_one()) {
 #pragma unroll 1
         for (int r = 0; r < 3; ++r) {
           const uint32_t a_r = a_base + (p.x_is_a ? r * tap_bytes : 0);
@@ -229,6 +280,30 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       const int rot = p.debug == 2 ? 0 : split;
       const int n_cb = p.n_cols >> 4;
 #pragma unroll 1
+      if (p.c8) {
+        // accumulator r, column block sc = tap (r, sc), 8 channels each: ws[tap][cout][8]
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * p.n_cols;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld16(taddr + c0, v);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int sc = (c0 >> 3) + h;
+                if (sc < 3) {
+                  float* dst = p.ws + ((long long)(r * 3 + sc) * p.Mtot + (m0 + row)) * 8;
+                  red_add_v4(dst, __uint_as_float(v[8 * h]), __uint_as_float(v[8 * h + 1]), __uint_as_float(v[8 * h + 2]), __uint_as_float(v[8 * h + 3]));
+                  red_add_v4(dst + 4, __uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5]), __uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7]));
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int rr = 0; rr < 3; ++rr) {
         const int r = (rr + rot) % 3;
         const int tap = r * 3 + s;
@@ -317,6 +392,21 @@ static int wg_encode(CUtensorMap* m, const void* x, int N, int H, int W, int C, 
   return FOSVOS_OK;
 }
 
+// first layer: the (N,H,W,8) frame as (8 W, H, N); box = one 16 x 8 patch with its halo, 10 pixels x 18 rows, no swizzle
+static int wg_encode_c8(CUtensorMap* m, const void* x, int N, int H, int W) {
+  EncodeTiledFn enc = wg_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
+  cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[3] = {80, 18, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wgrad first layer %dx%dx%d) failed: %d", N, H, W, (int)r); return FOSVOS_ERR_DRIVER; }
+  return FOSVOS_OK;
+}
+
 }  // namespace fosvos
 
 using namespace fosvos;
@@ -346,7 +436,9 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   p.x_is_a = wg_x_is_a(CinP, CoutP);
   p.Mtot = p.x_is_a ? CinP : CoutP;
   p.Ntot = p.x_is_a ? CoutP : CinP;
-  p.n_cols = p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
+  p.c8 = (CinP == 8 && !p.x_is_a && !getenv("FOSVOS_WG_NO_C8")) ? 1 : 0;
+  p.c8_lbo = WG_C8_ROW; p.c8_sbo = 16;
+  p.n_cols = p.c8 ? 32 : p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
   p.nb_n = (p.n_cols + 63) / 64;
   p.m_tiles = ceil_div(p.Mtot, 128);
   p.n_tiles = ceil_div(p.Ntot, p.n_cols);
@@ -357,6 +449,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
     const long long area = (long long)ceil_div(H, TH) * TH * ceil_div(W, TW) * TW;
     if (best_area < 0 || area < best_area) { best_area = area; best = sh; }
   }
+  if (p.c8) best = 3;                                 // 16 x 8 patches: the halo box layout is built for TW = 8
   p.tw_shift = best;
   const int TW = 1 << best, TH = 128 >> best;
   p.tiles_x = ceil_div(W, TW);
@@ -364,7 +457,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   p.patches = N * p.tiles_x * p.tiles_y;
   p.x_block = (TH + 2) * TW * 128;
   const int nb_x = p.x_is_a ? 2 : p.nb_n, nb_z = p.x_is_a ? p.nb_n : 2;
-  const int x_bytes = nb_x * p.x_block, z_bytes = nb_z * WG_PLAIN_BLOCK;
+  const int x_bytes = p.c8 ? WG_C8_BYTES : nb_x * p.x_block, z_bytes = nb_z * WG_PLAIN_BLOCK;
   p.a_bytes = p.x_is_a ? x_bytes : z_bytes;
   p.stage_bytes = x_bytes + z_bytes;
   p.stages = min(6, (220 * 1024 - 2048) / p.stage_bytes);
@@ -372,7 +465,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   // Split-K over pixel ranges.  Every CTA ends with 3 * 128 * n_cols fp32 reductions into the workspace, so the
   // split count trades tensor-core occupancy against reduction traffic: fill the machine once; go to a second
   // wave only while each CTA still has enough patches to amortise its epilogue.
-  const int items = p.m_tiles * p.n_tiles * 3;
+  const int items = p.m_tiles * p.n_tiles * (p.c8 ? 1 : 3);
   int splits = max(1, num_sms() / items);
   if ((long long)p.patches >= 16LL * 2 * num_sms() / items) splits = max(1, (2 * num_sms()) / items);
   if (const char* e = getenv("FOSVOS_WG_SPLITS")) { const int v = atoi(e); if (v > 0) splits = v; }
@@ -381,7 +474,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   { const char* e = getenv("FOSVOS_WG_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
   CUtensorMap mx, mz;
-  int rc = wg_encode(&mx, x, N, H, W, CinP, TW, TH + 2);
+  int rc = p.c8 ? wg_encode_c8(&mx, x, N, H, W) : wg_encode(&mx, x, N, H, W, CinP, TW, TH + 2);
   if (rc) return rc;
   rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, TH);
   if (rc) return rc;
