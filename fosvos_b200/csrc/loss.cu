@@ -27,17 +27,19 @@ constexpr int LOSS_MAX_BLOCKS = 160;            // ... but every block ends with
 // block, not three same-address double atomics) adds the slots up in a fixed order and finalises.
 __device__ __forceinline__ void loss_finish(LossAcc a, double* __restrict__ stats, float* __restrict__ loss, long long n,
                                             int size_average, bool counts_given) {
-  double pos = warp_sum((double)a.pos), sp = warp_sum((double)a.s_pos), sn = warp_sum((double)a.s_neg);
-  __shared__ double sm[3][LOSS_THREADS / 32];
+  // fp32 inside the block (<= a few 10^4 elements per block: counts stay exact, sums keep ~1e-6), double across blocks
+  float posf = warp_sum(a.pos), spf = warp_sum(a.s_pos), snf = warp_sum(a.s_neg);
+  __shared__ float sm[3][LOSS_THREADS / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { sm[0][wid] = pos; sm[1][wid] = sp; sm[2][wid] = sn; }
+  if (lane == 0) { sm[0][wid] = posf; sm[1][wid] = spf; sm[2][wid] = snf; }
   __syncthreads();
   if (wid == 0) {
-    pos = lane < LOSS_THREADS / 32 ? sm[0][lane] : 0.0;
-    sp = lane < LOSS_THREADS / 32 ? sm[1][lane] : 0.0;
-    sn = lane < LOSS_THREADS / 32 ? sm[2][lane] : 0.0;
-    pos = warp_sum(pos); sp = warp_sum(sp); sn = warp_sum(sn);
+    posf = lane < LOSS_THREADS / 32 ? sm[0][lane] : 0.f;
+    spf = lane < LOSS_THREADS / 32 ? sm[1][lane] : 0.f;
+    snf = lane < LOSS_THREADS / 32 ? sm[2][lane] : 0.f;
+    posf = warp_sum(posf); spf = warp_sum(spf); snf = warp_sum(snf);
+    const double pos = (double)posf, sp = (double)spf, sn = (double)snf;
     if (lane == 0) {
       double* slot = stats + 8 + 3 * blockIdx.x;
       slot[0] = pos; slot[1] = sp; slot[2] = sn;
