@@ -299,12 +299,13 @@ def side_roofline(net, frames, peaks):
     with torch.no_grad():
         _, _, _, saved = net._run_forward(frames, save=True)
         sps, params = saved["sps"], saved["params"]
-        ms = _time_ms(lambda: ops.side_fwd(sps, params, H, W, general=False, want_prob=True, want_mask=True), reps=10)
+        mode = 1 if net._side_general else (2 if net._side_separable else 0)      # the path the network itself takes
+        ms = _time_ms(lambda: ops.side_fwd(sps, params, H, W, general=mode, want_prob=True, want_mask=True), reps=10)
     esz = sps[0].element_size()
     low = sum(t.shape[1] * t.shape[2] for t in sps)
     bytes_per_frame = 16 * low * esz + 5 * H * W * 4 + H * W * 4 + H * W       # read sp; write 5 maps + prob + mask
     achieved = bytes_per_frame * n / (ms / 1e3) / 1e9
-    return dict(bound="hbm", kernel="side_heads_kernel + side_upsample_kernel", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
+    return dict(bound="hbm", kernel="side_heads_kernel + " + ("side_upsample_sep_kernel" if mode == 2 else "side_upsample_kernel"), achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                 frac=achieved / peaks["hbm_gbs"], traffic=None, batch=n, ms=ms, bytes_per_frame=bytes_per_frame)
 
 
@@ -392,7 +393,7 @@ def main():
     ap.add_argument("--iters", type=int, default=500)
     ap.add_argument("--avg-grad-every-n", type=int, default=5)
     ap.add_argument("--frames", type=int, default=80)
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--graph", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -56,6 +56,7 @@ SIGNATURES = {
     "fosvos_side_workspace_bytes": (C.c_size_t, [_vp, _vp, _i]),
     "fosvos_side_prepare": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fosvos_side_check_diagonal": (_i, [_vp, _vp, _vp]),
+    "fosvos_side_params_separable_flag": (_i, []),
     "fosvos_side_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fosvos_bal_loss_stats_bytes": (C.c_size_t, []),

@@ -77,6 +77,7 @@ class OSVOS_VGG(nn.Module):
         self._side_key = None
         self._side_params: Optional[torch.Tensor] = None
         self._side_general = False
+        self._side_separable = False
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -188,9 +189,13 @@ class OSVOS_VGG(nn.Module):
             if self._side_key is None or self._side_key[:4] != up_key:
                 # structure check of the up-sampling weights (one sync, only when they change)
                 self._side_general = bool(ops.side_check_diagonal([m.weight for m in self.upscale]).item() != 0)
+            recheck = self._side_key is None or self._side_key[:8] != key[:8]
             self._side_params = ops.side_params_prepare([m.weight for m in self.upscale], [m.weight for m in self.upscale_],
                                                         [m.weight for m in self.score_dsn], [m.bias for m in self.score_dsn],
                                                         self.fuse.weight, self.fuse.bias, out=self._side_params)
+            if recheck:
+                # exact separability of the two shared kernels (one more sync, only when up-sampling weights change)
+                self._side_separable = (not self._side_general) and ops.side_separable(self._side_params)
             self._side_key = key
         return self._side_params
 
@@ -264,7 +269,8 @@ class OSVOS_VGG(nn.Module):
         if aux is not None:
             main.wait_stream(aux)
         params = self._side()
-        outs, prob, mask = ops.side_fwd(sps, params, H, W, general=self._side_general, want_prob=want_prob, want_mask=want_mask)
+        mode = 1 if self._side_general else (2 if self._side_separable else 0)
+        outs, prob, mask = ops.side_fwd(sps, params, H, W, general=mode, want_prob=want_prob, want_mask=want_mask)
         saved = None
         if save:
             saved = dict(conv_in=conv_in, conv_out=conv_out, pool_in=pool_in, stage_out=stage_out, sps=sps, H=H, W=W,

@@ -190,9 +190,16 @@ def side_check_diagonal(upscale_w: Sequence[torch.Tensor]) -> torch.Tensor:
     return flag
 
 
-def side_fwd(sp: Sequence[torch.Tensor], params: torch.Tensor, H: int, W: int, general: bool = False,
+def side_separable(params: torch.Tensor) -> bool:
+    """True when both shared up-sampling kernels of a prepared parameter block factor exactly (host sync)."""
+    return float(params[L.lib().fosvos_side_params_separable_flag()].item()) == 0.0
+
+
+def side_fwd(sp: Sequence[torch.Tensor], params: torch.Tensor, H: int, W: int, general=False,
              want_prob: bool = False, want_mask: bool = False):
-    """-> ([side0..3, fused] each (N,1,H,W) fp32, prob or None, mask or None)"""
+    """-> ([side0..3, fused] each (N,1,H,W) fp32, prob or None, mask or None)
+    general: False/0 = shared-kernel fast path, True/1 = any up-sampling weights, 2 = separable fast path
+    (only when ``side_separable(params)``)."""
     dev = params.device
     L.require_device(dev)
     n = sp[0].shape[0]
@@ -205,7 +212,7 @@ def side_fwd(sp: Sequence[torch.Tensor], params: torch.Tensor, H: int, W: int, g
     mask = torch.empty((n, 1, H, W), dtype=torch.uint8, device=dev) if want_mask else None
     ha, wa = L.int_array(hs), L.int_array(ws)
     wsb = L.lib().fosvos_side_workspace_bytes(ha, wa, n)
-    workspace = None if general else torch.empty(wsb, dtype=torch.uint8, device=dev)
+    workspace = None if int(general) == 1 else torch.empty(wsb, dtype=torch.uint8, device=dev)
     L.check(L.lib().fosvos_side_fwd(L.ptr_array(sp), ha, wa, params.data_ptr(), L.ptr_array(outs), L.ptr(prob), L.ptr(mask),
                                     L.ptr(workspace), int(general), n, H, W, L.dtype_code(sp[0].dtype), L.stream()), "side_fwd")
     return outs, prob, mask

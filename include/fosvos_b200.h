@@ -167,6 +167,11 @@ int fosvos_maxpool2x2_bwd_add(const void* x, const void* dy, const void* add, vo
  * and fuse.bias.  This is exact for ANY upscale weights (no diagonality assumption).
  * fosvos_side_params_bytes() gives the block size. */
 size_t fosvos_side_params_bytes(void);
+/* Float index inside the parameter block of the "not separable" counter written by fosvos_side_prepare:
+ * 0 <=> both shared up-sampling kernels factor exactly as a[ky]*b[kx] and fosvos_side_fwd may run with
+ * general = 2 (two packed FMAs per stage and pixel).  general: 0 = shared-kernel fast path, 1 = any
+ * up-sampling weights, 2 = separable fast path. */
+int fosvos_side_params_separable_flag(void);
 int fosvos_side_prepare(const float* const* upscale_w /*4: (16,16,k,k)*/,
                         const float* const* upscale1_w /*4: (1,1,k,k)*/,
                         const float* const* score_w /*4: (1,16,1,1)*/,

@@ -306,7 +306,7 @@ def _side_params(sd):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("general", [False, True])
+@pytest.mark.parametrize("general", [False, True, 2])
 @pytest.mark.parametrize("HW", [(48, 72), (45, 70), (33, 17)])
 def test_side_chain_forward(dt, general, HW):
     H, W = HW
@@ -315,6 +315,7 @@ def test_side_chain_forward(dt, general, HW):
     ref = _side_ref([r(t) for t in sp], sd, H, W)
     params, dsd = _side_params(sd)
     assert int(ops.side_check_diagonal([dsd[f"upscale.{i}.weight"] for i in range(4)]).item()) == 0
+    assert ops.side_separable(params)              # the bilinear kernels of interp_surgery factor exactly in fp32
     outs, prob, mask = ops.side_fwd([_nhwc(t, dt) for t in sp], params, H, W, general=general, want_prob=True, want_mask=True)
     for a, b in zip(outs, ref):
         assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=2e-5), float((a.cpu() - b).abs().max())
@@ -341,6 +342,7 @@ def test_side_chain_fast_path_arbitrary_shared_kernel(HW):
     ref = _side_ref(sp, sd, H, W)
     params, dsd = _side_params(sd)
     assert int(ops.side_check_diagonal([dsd[f"upscale.{i}.weight"] for i in range(4)]).item()) == 0
+    assert not ops.side_separable(params)          # a random k x k kernel has full rank: stays on the phase-table path
     outs, prob, mask = ops.side_fwd([_nhwc(t, torch.float32) for t in sp], params, H, W, general=False, want_prob=True, want_mask=True)
     for a, b in zip(outs, ref):
         assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=5e-5), float((a.cpu() - b).abs().max())

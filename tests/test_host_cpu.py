@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/fosvos_b200.h but not exported"
     assert sorted(L.SIGNATURES) == names, "ctypes binding and header disagree"
     assert L.lib().fosvos_abi_version() >= 1
-    # scalars + k x k tables (g1, gs, G[16]) per stage, then the two 340-phase float4 tap tables of the fast path
-    assert L.lib().fosvos_side_params_bytes() == 4 * (4 + 4 * 36 + 18 * (16 + 64 + 256 + 1024)) + 2 * 16 * (4 + 16 + 64 + 256)
+    # scalars + k x k tables (g1, gs, G[16]) per stage, then the two 340-phase float4 tap tables of the fast path, the 2 x 30 float4 separable tables and the flag
+    assert L.lib().fosvos_side_params_bytes() == 4 * (4 + 4 * 36 + 18 * (16 + 64 + 256 + 1024)) + 2 * 16 * (4 + 16 + 64 + 256) + 2 * 16 * 30 + 16
 
 
 def test_no_cpu_fallback():

@@ -51,6 +51,9 @@ for dt in (torch.bfloat16, torch.float32):
     t = timeit(lambda: ops.side_fwd(sps, params, H, W, general=False, want_prob=True, want_mask=True))
     b = (16 * low * sps[0].element_size() + 5 * H * W * 4 + H * W * 4 + H * W) * batch
     print(f"side_fwd[{dt}] batch {batch}: {t:.1f} us  {b / t / 1e3:.0f} GB/s ({b / 1e6:.1f} MB)")
+    if ops.side_separable(params):
+        t = timeit(lambda: ops.side_fwd(sps, params, H, W, general=2, want_prob=True, want_mask=True))
+        print(f"side_fwd[{dt}] separable path: {t:.1f} us  {b / t / 1e3:.0f} GB/s")
     t = timeit(lambda: ops.side_fwd(sps, params, H, W, general=False))
     b = (16 * low * sps[0].element_size() + 5 * H * W * 4) * batch
     print(f"side_fwd[{dt}] no prob/mask: {t:.1f} us  {b / t / 1e3:.0f} GB/s")
