@@ -145,7 +145,8 @@ def run_ours(args):
     from fosvos_b200.online import OnlineTrainer
     net = new_net()
     sd_dev = {k: v.to(dev) for k, v in sd0.items()}
-    trainer = OnlineTrainer(net, H, W, args.avg_grad_every_n, FB.get_optimizer_online(net), use_graph=bool(args.graph))
+    trainer = OnlineTrainer(net, H, W, args.avg_grad_every_n, FB.get_optimizer_online(net), use_graph=bool(args.graph),
+                            fuse_window=bool(args.fuse_window))
     masks_out_pin = torch.empty((args.frames, 1, H, W), dtype=torch.uint8).pin_memory()
 
     def sequence_job(host: bool):
@@ -219,6 +220,8 @@ def run_ours(args):
             "config": {"workload": f"configs[1]: one-shot online fine-tune ({args.iters} SGD iters, batch 1, avg_grad_every_n={args.avg_grad_every_n}) + inference over a {args.frames}-frame 480x854 sequence, per GPU",
                        "frames_per_sequence": args.frames, "finetune_iters": args.iters, "inference_batch": args.batch,
                        "sharding": "by sequence, one per rank, no collective", "cuda_graph": bool(args.graph),
+                       "fuse_window": bool(args.fuse_window),
+                       "fuse_window_note": "the 5 micro-iterations of an accumulation window (same weights, summed gradients) run as one batched forward/backward; every iteration's frame is computed in full; --fuse-window 0 gives the strictly sequential loop",
                        "l2": "each step touches > 126 MB of distinct activations (52 MB/layer at stage 0); no explicit flush"},
             "inference_fps": world * args.steps * args.frames / (t_inf_max / 1e3),
             "finetune_s_per_sequence": t_ft_max / 1e3 / args.steps,
@@ -395,6 +398,8 @@ def main():
     ap.add_argument("--frames", type=int, default=80)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--fuse-window", type=int, default=1,
+                    help="run the avg_grad_every_n micro-iterations between two optimizer steps as one batched pass (same gradients)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,6 +56,8 @@ constexpr int TC_BIAS_BYTES = 2048;  // all CoutP <= 512 biases, staged once per
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one 64-channel output slab of a tile
 constexpr int MODE_GENERIC = 0, MODE_C8 = 1, MODE_HALO = 2;
+constexpr int TC_FLAG_SKIP_B = 1 << 21;          // internal (FOSVOS_TC_SKIP_B=1): timing experiment, weight tiles are not loaded
+constexpr int TC_FLAG_SKIP_A = 1 << 22;          // internal (FOSVOS_TC_SKIP_A=1): timing experiment, activation boxes are not loaded
 constexpr int TC_FLAG_MASK_IN_REGS = 1 << 20;    // internal (FOSVOS_TC_MASK_REGS=1): apply the ReLU mask in the register phase
 constexpr int HALO_A_BYTES = 20 * 1024;          // (TH+2) x TW x 128 B: 18 KB for 16x8 patches, 20 KB for 8x16
 constexpr int C8_ROW_BYTES = (8 + 2) * 16;       // one image row of the halo tile: 10 pixels x 8 channels
@@ -213,8 +215,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           for (int s = 0; s < 3; ++s) {
             ptx::mbar_wait_a(bar_empty, phase ^ 1);
             if (ptx::elect_one()) {
-              ptx::mbar_expect_tx_a(bar_full, p.halo_bytes);
-              ptx::tma_load_4d_a(a_dst, &map_x, bar_full, c, x0 + s - 1, y0 - 1, n);
+              if (p.flags & TC_FLAG_SKIP_A) {
+                ptx::mbar_expect_tx_a(bar_full, 0);
+              } else {
+                ptx::mbar_expect_tx_a(bar_full, p.halo_bytes);
+                ptx::tma_load_4d_a(a_dst, &map_x, bar_full, c, x0 + s - 1, y0 - 1, n);
+              }
             }
             __syncwarp();
             a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
@@ -222,8 +228,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             for (int r = 0; r < 3; ++r) {
               ptx::mbar_wait_a(bbar_empty, bphase ^ 1);
               if (ptx::elect_one()) {
-                ptx::mbar_expect_tx_a(bbar_full, Cfg::B_BYTES);
-                ptx::tma_load_2d_a(b_dst, &map_w, bbar_full, (3 * r + s) * p.cin_pad + c, n0);
+                if (p.flags & TC_FLAG_SKIP_B) {
+                  ptx::mbar_expect_tx_a(bbar_full, 0);
+                } else {
+                  ptx::mbar_expect_tx_a(bbar_full, Cfg::B_BYTES);
+                  ptx::tma_load_2d_a(b_dst, &map_w, bbar_full, (3 * r + s) * p.cin_pad + c, n0);
+                }
               }
               __syncwarp();
               b_dst += Cfg::B_BYTES; bbar_full += 8; bbar_empty += 8;
@@ -693,6 +703,8 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   p.taps = taps;
   p.flags = flags & 0xffff;
   if ((flags & FOSVOS_CONV_MASK) && getenv("FOSVOS_TC_MASK_REGS")) p.flags |= TC_FLAG_MASK_IN_REGS;
+  if (getenv("FOSVOS_TC_SKIP_B")) p.flags |= TC_FLAG_SKIP_B;
+  if (getenv("FOSVOS_TC_SKIP_A")) p.flags |= TC_FLAG_SKIP_A;
   const long long m_tiles = (long long)N * p.tiles_x * p.tiles_y;
   // N tile: minimise waves x cycles per tile.  One M=128 tcgen05.mma costs max(N/2, ~57) cycles
   // (tools/exp/mma_issue.cu), so tiles narrower than 128 only pay when they fill an otherwise idle machine.

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 bal_loss_fwd_kernel(const float* __restrict__ out, const float* __restrict__ lab, long long n, int size_average,
                     double* __restrict__ stats, float* __restrict__ loss) {
   LossAcc a{0.f, 0.f, 0.f};
-  const long long n4 = n / 4;
+  // float4 path only for 16-byte aligned maps (a frame slice of an odd-sized batch is not)
+  const long long n4 = (((uintptr_t)out | (uintptr_t)lab) & 15) == 0 ? n / 4 : 0;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   long long i = tid;
   for (; i + nth < n4; i += 2 * nth) {           // two independent 16-byte loads per stream in flight
@@ -129,7 +130,7 @@ bal_loss_fused_kernel(const float* __restrict__ out, const float* __restrict__ l
     const float sg = x >= 0.f ? r : t * r;
     return l >= 0.5f ? w1 * (sg - 1.f) : w0 * sg;
   };
-  const long long n4 = n / 4;
+  const long long n4 = (((uintptr_t)out | (uintptr_t)lab | (uintptr_t)dx) & 15) == 0 ? n / 4 : 0;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i < n4; i += nth) {
     const float4 x = reinterpret_cast<const float4*>(out)[i];
@@ -154,7 +155,7 @@ bal_loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ lab
     const float s = x >= 0.f ? 1.f / (1.f + t) : t / (1.f + t);
     return l >= 0.5f ? w1 * (s - 1.f) : w0 * s;
   };
-  const long long n4 = n / 4;
+  const long long n4 = (((uintptr_t)out | (uintptr_t)lab | (uintptr_t)dx) & 15) == 0 ? n / 4 : 0;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i < n4; i += nth) {
     const float4 x = reinterpret_cast<const float4*>(out)[i];
@@ -219,7 +220,6 @@ static int loss_blocks(long long numel) { return (int)min((long long)min(num_sms
 int fosvos_bal_loss_fwd(const float* output, const float* label, long long numel, int size_average, double* stats,
                         float* loss, fosvos_stream_t stream) {
   FOSVOS_REQUIRE(output && label && stats && loss && numel > 0, "bal_loss_fwd: bad arguments");
-  FOSVOS_REQUIRE(((uintptr_t)output & 15) == 0 && ((uintptr_t)label & 15) == 0, "bal_loss_fwd: pointers must be 16-byte aligned");
   cudaMemsetAsync(stats, 0, 8 * sizeof(double), as_stream(stream));
   bal_loss_fwd_kernel<<<loss_blocks(numel), LOSS_THREADS, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, loss);
   return check_launch("bal_loss_fwd");
@@ -228,8 +228,6 @@ int fosvos_bal_loss_fwd(const float* output, const float* label, long long numel
 int fosvos_bal_loss_fwd_bwd(const float* output, const float* label, long long numel, int size_average, double* stats,
                             float* loss, const float* grad_out, float grad_scale, float* dx, fosvos_stream_t stream) {
   FOSVOS_REQUIRE(output && label && stats && loss && dx && numel > 0, "bal_loss_fwd_bwd: bad arguments");
-  FOSVOS_REQUIRE(((uintptr_t)output & 15) == 0 && ((uintptr_t)label & 15) == 0 && ((uintptr_t)dx & 15) == 0,
-                 "bal_loss_fwd_bwd: pointers must be 16-byte aligned");
   bal_loss_fused_kernel<<<loss_blocks(numel), LOSS_THREADS, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, loss,
                                                                                    grad_out, grad_scale, dx);
   return check_launch("bal_loss_fwd_bwd");
@@ -239,8 +237,6 @@ int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel
                         const double* stats, const float* grad_out, float grad_scale, float* dx,
                         fosvos_stream_t stream) {
   FOSVOS_REQUIRE(output && label && stats && dx && numel > 0, "bal_loss_bwd: bad arguments");
-  FOSVOS_REQUIRE(((uintptr_t)output & 15) == 0 && ((uintptr_t)label & 15) == 0 && ((uintptr_t)dx & 15) == 0,
-                 "bal_loss_bwd: pointers must be 16-byte aligned");
   const int blocks = (int)min((long long)num_sms() * 4, ceil_div_ll(numel, 1024));
   bal_loss_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, grad_out,
                                                             grad_scale, dx);

@@ -101,8 +101,13 @@ class OnlineTrainer:
 
     def __init__(self, net: OSVOS_VGG, height: int, width: int, avg_grad_every_n: int = 5,
                  optimizer: Optional[FusedSGD] = None, use_graph: bool = True, deep_supervision: Optional[float] = None,
-                 data_parallel: bool = False, world_size: int = 1):
-        """``data_parallel``: offline parent training sharded over ``world_size`` ranks (one process per GPU): every
+                 data_parallel: bool = False, world_size: int = 1, fuse_window: bool = True):
+        """``fuse_window``: the ``avg_grad_every_n`` micro-iterations between two optimizer steps all see the SAME weights
+        and their gradients are summed, so they are independent of each other: run them as ONE batched
+        forward/backward over the window's frames (every frame is still computed in full, each with its own loss and
+        label statistics; the accumulated gradient is the same sum in a different fp32 order).  At batch 1 a third of
+        every layer's time is launch, prologue, pipeline fill and tail waves -- the window amortises them.
+        ``data_parallel``: offline parent training sharded over ``world_size`` ranks (one process per GPU): every
         rank runs ``avg_grad_every_n // world_size`` micro-iterations on its own frames, gradients (scaled by
         1/avg_grad_every_n as in the reference) are summed with ONE all-reduce of a flat fp32 buffer, then every
         rank applies the same optimizer step."""
@@ -120,8 +125,13 @@ class OnlineTrainer:
         self.optimizer = optimizer if optimizer is not None else get_optimizer_online(net)
         self.fused = isinstance(self.optimizer, FusedSGD)
         self.use_graph = bool(use_graph) and self.fused
-        self.frame = torch.zeros((1, net.stages[0][0].in_channels, height, width), dtype=torch.float32, device=dev)
-        self.mask = torch.zeros((1, 1, height, width), dtype=torch.float32, device=dev)
+        self.fuse = bool(fuse_window) and self.n > 1
+        slots = self.n if self.fuse else 1
+        # one resident slot per micro-iteration of a window; slot 0 doubles as the single-iteration buffers
+        self.frames = torch.zeros((slots, net.stages[0][0].in_channels, height, width), dtype=torch.float32, device=dev)
+        self.masks = torch.zeros((slots, 1, height, width), dtype=torch.float32, device=dev)
+        self.frame, self.mask = self.frames[0:1], self.masks[0:1]
+        self.window_losses = torch.zeros(slots, dtype=torch.float32, device=dev)
         params = dict(net.named_parameters())
         self.grads: Dict[str, torch.Tensor] = {}
         self.flat_grad = None
@@ -149,17 +159,46 @@ class OnlineTrainer:
                     self.wgrad_ws[name[:-len(".weight")]] = ops.wgrad_workspace(ops.pad8(cin), ops.pad8(cout), dev)
         self._fold_table = None
         # label counts of the resident mask: they only change with set_frame(), so loss and gradient are ONE pass
-        self.loss_stats = torch.zeros(L.lib().fosvos_bal_loss_stats_bytes() // 8, dtype=torch.float64, device=dev)
-        ops.bal_loss_fwd(self.mask, self.mask, False, stats=self.loss_stats)
+        self.loss_stats_all = torch.zeros((slots, L.lib().fosvos_bal_loss_stats_bytes() // 8), dtype=torch.float64, device=dev)
+        self.loss_stats = self.loss_stats_all[0]
+        self._label_counts()
         self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
         self.last_loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.counter = 0
         self._micro_graph = None
+        self._window_graph = None
         self._step_graph = None
         self._calls_micro = 0
+        self._calls_window = 0
         self._calls_step = 0
 
     # ---------------------------------------------------------------- pieces
+    def _label_counts(self) -> None:
+        for i in range(self.masks.shape[0]):
+            ops.bal_loss_fwd(self.masks[i:i + 1], self.masks[i:i + 1], False, stats=self.loss_stats_all[i])
+
+    def _window(self) -> None:
+        """All micro-iterations of one accumulation window as one batched pass (see ``fuse_window``)."""
+        net = self.net
+        n = self.frames.shape[0]
+        outs, _, _, saved = net._run_forward(self.frames, save=True)
+        douts: List[Optional[torch.Tensor]] = [None] * 5
+        maps = [4] if self.deep_w is None else [4, 0, 1, 2, 3]
+        for j in maps:
+            douts[j] = torch.empty_like(outs[j])
+        for i in range(n):
+            # the class-balanced loss normalises by the label counts of ITS frame (osvos_layers.py:26-39): per-frame calls
+            total = None
+            for j in maps:
+                w = None if j == 4 else self.deep_w
+                lj, _ = ops.bal_loss_fwd_bwd(outs[j][i:i + 1], self.masks[i:i + 1], False, self.loss_stats_all[i], w, self.scale,
+                                             out=douts[j][i:i + 1])
+                total = lj if total is None else total + self.deep_w * lj
+            self.window_losses[i].copy_(total)
+        self.last_loss.copy_(self.window_losses[n - 1])
+        self.loss_sum.add_(self.window_losses.sum())
+        net._run_backward(saved, douts, self.grads, self.wgrad_ws)
+
     def _micro(self) -> None:
         net = self.net
         outs, _, _, saved = net._run_forward(self.frame, save=True)
@@ -196,41 +235,51 @@ class OnlineTrainer:
             for g in self.grads.values():
                 g.zero_()
 
-    def _capture(self) -> None:
-        """Warm up once (packs weights, sizes the allocator), then capture both graphs."""
+    def _capture(self, window: bool) -> None:
+        """Warm up once (packs weights, sizes the allocator), then capture the graph of one micro-iteration or of one
+        fused window, and (first time) the optimizer-step graph."""
+        import os
+        assert self.counter == 0, "graphs are captured at a window boundary (the warm-up pass clears the gradient accumulators)"
+        body = self._window if window else self._micro
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             c0 = L.CALLS[0]
-            self._micro()
-            self._calls_micro = L.CALLS[0] - c0
+            saved_sum = self.loss_sum.clone()
+            body()
+            calls = L.CALLS[0] - c0
             for g in self.grads.values():
                 g.zero_()
             for ws in (self.wgrad_ws or {}).values():
                 ws.zero_()
+            self.loss_sum.copy_(saved_sum)
             self.optimizer._ensure_table()          # momentum buffers + device table exist before capture
             if self.wgrad_ws and self._fold_table is None:
                 self._fold_table = ops.fold_table([(ws, self.grads[name + ".weight"]) for name, ws in self.wgrad_ws.items()],
                                                   self.frame.device)
             _repack_in_place(self.net)              # builds the multi-tensor repack table (host -> device copies)
         torch.cuda.current_stream().wait_stream(s)
-        self._micro_graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
+        pool = next((g.pool() for g in (self._micro_graph, self._window_graph, self._step_graph) if g is not None), None)
         # captured on a high-priority stream: the dependency chain (forward, data gradients) wins the SMs over the
         # weight gradients / side branches that the network issues on its default-priority auxiliary stream
-        import os
         hp = torch.cuda.Stream(priority=-1 if os.environ.get("FOSVOS_HP", "1") != "0" else 0)
         hp.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.graph(self._micro_graph, stream=hp):
-            self._micro()
+        with torch.cuda.graph(graph, stream=hp, **({} if pool is None else {"pool": pool})):
+            body()
         torch.cuda.current_stream().wait_stream(hp)
-        c0 = L.CALLS[0]
-        self._step_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._step_graph, pool=self._micro_graph.pool()):
-            self._step()
-        self._calls_step = L.CALLS[0] - c0
+        if window:
+            self._window_graph, self._calls_window = graph, calls
+        else:
+            self._micro_graph, self._calls_micro = graph, calls
+        if self._step_graph is None:
+            c0 = L.CALLS[0]
+            self._step_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._step_graph, pool=graph.pool()):
+                self._step()
+            self._calls_step = L.CALLS[0] - c0
         # capture does not execute: gradients are still zero, parameters untouched; versions were bumped
         _sync_cache_keys(self.net)
-        self.loss_sum.zero_()
 
     # ---------------------------------------------------------------- public
     def reset(self, state_dict: Optional[dict] = None) -> None:
@@ -255,38 +304,66 @@ class OnlineTrainer:
             self.net._side()                   # outside any graph) and rebuild the parameter block in place
 
     def set_frame(self, frame: torch.Tensor, mask: torch.Tensor) -> None:
-        """Copy the annotated frame (1,3,H,W) and its mask (1,1,H,W) into the resident buffers
-        (host tensors are uploaded; pinned ones asynchronously)."""
+        """Copy the annotated frame (1,3,H,W) and its mask (1,1,H,W) into the resident buffers -- into every slot of
+        the window: each micro-iteration reads its own copy (host tensors are uploaded; pinned ones asynchronously)."""
         self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)
         self.mask.copy_(mask.reshape(self.mask.shape), non_blocking=True)
-        ops.bal_loss_fwd(self.mask, self.mask, False, stats=self.loss_stats)      # label counts of the new mask
+        for i in range(1, self.frames.shape[0]):
+            self.frames[i:i + 1].copy_(self.frame)
+            self.masks[i:i + 1].copy_(self.mask)
+        self._label_counts()                                                      # label counts of the new mask(s)
+
+    def set_frames(self, frames: torch.Tensor, masks: torch.Tensor) -> None:
+        """Distinct frames for the micro-iterations of a window (e.g. flipped copies): (n,3,H,W) and (n,1,H,W)."""
+        self.frames.copy_(frames.reshape(self.frames.shape), non_blocking=True)
+        self.masks.copy_(masks.reshape(self.masks.shape), non_blocking=True)
+        self._label_counts()
+
+    def _optimizer_step(self) -> None:
+        self._fold_wgrads()
+        if self.data_parallel:
+            allreduce_flat(self.flat_grad)
+        if self.use_graph:
+            self._step_graph.replay()
+            L.CALLS[0] += self._calls_step
+            for p in self.net.parameters():
+                torch.autograd.graph.increment_version(p)
+            _sync_cache_keys(self.net)
+        else:
+            self._step()
 
     def run(self, n_iters: int, losses_out: Optional[list] = None) -> torch.Tensor:
-        if self.use_graph and self._micro_graph is None:
-            self._capture()
-        elif self.use_graph and not _keys_current(self.net):
+        if self.use_graph and (self._micro_graph is not None or self._window_graph is not None) and not _keys_current(self.net):
             _repack_in_place(self.net)          # parameters were changed from outside since the last replay
-        for _ in range(n_iters):
+        done = 0
+        while done < n_iters:
+            if self.fuse and self.counter == 0 and n_iters - done >= self.n:
+                # a whole accumulation window: one batched pass
+                if self.use_graph:
+                    if self._window_graph is None:
+                        self._capture(window=True)
+                    self._window_graph.replay()
+                    L.CALLS[0] += self._calls_window
+                else:
+                    self._window()
+                if losses_out is not None:
+                    losses_out.extend(float(v) for v in self.window_losses.tolist())
+                done += self.n
+                self._optimizer_step()
+                continue
             if self.use_graph:
+                if self._micro_graph is None:
+                    self._capture(window=False)
                 self._micro_graph.replay()
                 L.CALLS[0] += self._calls_micro
             else:
                 self._micro()
             if losses_out is not None:
                 losses_out.append(float(self.last_loss.item()))
+            done += 1
             self.counter += 1
             if self.counter % self.n == 0:
-                self._fold_wgrads()
-                if self.data_parallel:
-                    allreduce_flat(self.flat_grad)
-                if self.use_graph:
-                    self._step_graph.replay()
-                    L.CALLS[0] += self._calls_step
-                    for p in self.net.parameters():
-                        torch.autograd.graph.increment_version(p)
-                    _sync_cache_keys(self.net)
-                else:
-                    self._step()
+                self._optimizer_step()
                 self.counter = 0
         return self.loss_sum
 

@@ -339,3 +339,37 @@ def test_finetune_at_augmented_frame_sizes(hw):
     for k in ["stages.0.0.weight", "stages.2.3.weight", "stages.4.5.bias", "side_prep.3.weight", "fuse.weight"]:
         d, dr = mine[k].cpu() - sd[k], ref_sd[k] - sd[k]
         assert float((d - dr).abs().max()) <= 5e-3 * float(dr.abs().max()) + 1e-12, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_window_equals_sequential_micro_iterations(precision):
+    """The micro-iterations between two optimizer steps see the same weights and their gradients are summed: running
+    them as ONE batched pass over the window's (distinct) frames gives the losses and the update of the sequential
+    loop of train_online.py:75-101."""
+    from fosvos_b200.online import OnlineTrainer
+    H, W, n = 45, 70, 3
+    _, _, sd = _case(_load("fwd_45x70_random.pt"))
+    frames = torch.cat([synth.make_frame(2, f, H, W, noise=True)[0] for f in range(n)])
+    masks = torch.cat([synth.make_frame(2, f, H, W, noise=True)[1] for f in range(n)])
+    results = []
+    for fuse in (False, True):
+        net = _net(sd, precision)
+        tr = OnlineTrainer(net, H, W, n, FB.get_optimizer_online(net, learning_rate=1e-6), use_graph=True, fuse_window=fuse)
+        losses = []
+        for step in range(2):
+            if fuse:
+                tr.set_frames(frames.to(DEV), masks.to(DEV))
+                tr.run(n, losses)
+            else:
+                for i in range(n):
+                    tr.set_frame(frames[i:i + 1].to(DEV), masks[i:i + 1].to(DEV))
+                    tr.run(1, losses)
+        results.append((losses, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}))
+    (l0, w0), (l1, w1) = results
+    assert len(l0) == len(l1) == 2 * n
+    assert np.allclose(l0, l1, rtol=1e-5 if precision == "fp32" else 2e-2), (l0, l1)
+    for k in ["stages.0.0.weight", "stages.1.3.weight", "stages.4.5.weight", "stages.3.1.bias", "side_prep.0.weight", "fuse.weight"]:
+        d0, d1 = w0[k] - sd[k], w1[k] - sd[k]
+        # (cancelling sums over noise frames: the fp32 summation ORDER differs between the two schedules)
+        tol = (2e-3 if precision == "fp32" else 5e-2) * float(d0.abs().max()) + 1e-12
+        assert float((d0 - d1).abs().max()) <= tol, (k, float((d0 - d1).abs().max()), float(d0.abs().max()))
