@@ -206,6 +206,21 @@ def run_ours(args):
                h2d_bytes_per_step=int(args.frames * 3 * H * W + 4 * H * W * 4),      # uint8 frames + the fp32 annotated frame and mask
                d2h_bytes_per_step=int(args.frames * H * W))
 
+    # ---- for transparency: the strictly sequential loop (one micro-iteration per pass), one sequence, not part of `value`
+    t_seq_ms = None
+    if args.fuse_window and rank == 0:
+        net_s = new_net()
+        tr_s = OnlineTrainer(net_s, H, W, args.avg_grad_every_n, FB.get_optimizer_online(net_s), use_graph=bool(args.graph), fuse_window=False)
+        tr_s.set_frame(frames_d[0:1], masks_d[0:1])
+        tr_s.run(2 * args.avg_grad_every_n)
+        tr_s.reset(sd_dev)
+        tr_s.set_frame(frames_d[0:1], masks_d[0:1])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); tr_s.run(args.iters); e1.record(); torch.cuda.synchronize()
+        t_seq_ms = e0.elapsed_time(e1)
+        del tr_s, net_s
+
     out = None
     if rank == 0:
         # ---- roofline of the dominant kernel family (3x3 conv implicit GEMM), measured live -------
@@ -226,6 +241,7 @@ def run_ours(args):
             "inference_fps": world * args.steps * args.frames / (t_inf_max / 1e3),
             "finetune_s_per_sequence": t_ft_max / 1e3 / args.steps,
             "finetune_tflops": ITER_GFLOP * args.iters * args.steps / (t_ft_max / 1e3) / 1e3 if t_ft_max > 0 else None,
+            "finetune_s_per_sequence_sequential_loop": None if t_seq_ms is None else t_seq_ms / 1e3,
             "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks, "roofline": roof, "roofline_side_chain": side, "roofline_loss": loss_roof,
             "cpu_baseline": cpu, "peaks": peaks,
         }

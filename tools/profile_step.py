@@ -1,5 +1,5 @@
-"""Small fixed workload for ncu: `reps` x (one 8-frame inference batch + one fine-tune micro-iteration
-+ one optimizer step) at 480x854, bf16.  Used for the launch list and the --set full captures."""
+"""Small fixed workload for ncu: `reps` x (one 8-frame inference batch + one fine-tune accumulation window of
+5 micro-iterations + one optimizer step) at 480x854, bf16.  Used for the launch list and the --set full captures."""
 import os
 import sys
 
@@ -25,6 +25,6 @@ for _ in range(reps):
     if mode in ("both", "inf"):
         net.predict(xb)
     if mode in ("both", "ft"):
-        FB.finetune(net, x, m, 1, 1, optimizer=opt)
+        FB.finetune(net, x, m, 5, 5, optimizer=opt)      # one accumulation window (5 micro-iterations, one batched pass) + step
 torch.cuda.synchronize()
 print("profile_step ok")
