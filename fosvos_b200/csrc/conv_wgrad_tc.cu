@@ -24,6 +24,10 @@
 // LBO = 160 (next image row = next 8 pixels along K) one MMA covers the three taps of a kernel row (N = 32, the
 // fourth block is ignored), so a patch is visited once (not once per kernel column) and dZ is read once.
 //
+// Cin = 64 (`pair`): a 64-channel operand fills only half of the M = 128 rows.  With X on M the two halves of A are
+// the SAME 64 channels under two horizontal shifts (two halo boxes, LBO apart): rows 0..63 accumulate kernel column
+// s, rows 64..127 column s + 1 -- two kernel columns per pass, so the nine taps take two passes instead of three.
+//
 // Bias gradient db[co] = sum_p dZ[p][co]: the dZ boxes are in shared memory anyway, so the four epilogue
 // warps, otherwise idle until the accumulators are complete, sum them on the side; the CTAs that see the
 // same dZ tile (three kernel columns x the tiles of the X-channel dimension) take every share-th patch each.
@@ -54,6 +58,7 @@ struct WgParams {
   int stages, stage_bytes, a_bytes;
   int x_block;               // bytes of one shifted 64-channel box: (TH+2)*TW*128
   int c8;                    // first-layer mode (see the header comment)
+  int pair;                  // Cin == 64: the two 64-row halves of A are two kernel columns of the same channels
   int c8_lbo, c8_sbo;        // descriptor strides of its un-swizzled X operand (160 / 16)
   int debug;                 // FOSVOS_WG_DEBUG: 1 = skip the reductions (timing experiments only), 2 = no start rotation
 };
@@ -100,16 +105,17 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   // work item
   int item = blockIdx.x;
   const int split = item % p.splits; item /= p.splits;
-  const int s = p.c8 ? 0 : item % 3;
-  if (!p.c8) item /= 3;
+  const int n_s = p.c8 ? 1 : p.pair ? 2 : 3;        // passes over the kernel columns
+  const int s = p.pair ? 2 * (item % n_s) : item % n_s;   // (first) kernel column of this pass
+  item /= n_s;
   const int nt = item % p.n_tiles;
   const int mt = item / p.n_tiles;
   // Bias gradient: the CTAs (s, other-dimension tile) that share this CTA's dZ tile split its patches between them
   // (patch pt belongs to CTA pt % share == share_id), so the extra shared-memory reads are spread evenly instead of
   // slowing one CTA in three -- the MMA stream already uses the full shared-memory bandwidth.
   const bool do_bias = p.db != nullptr;
-  const int share = (p.c8 ? 1 : 3) * (p.x_is_a ? p.m_tiles : p.n_tiles);
-  const int share_id = s * (p.x_is_a ? p.m_tiles : p.n_tiles) + (p.x_is_a ? mt : nt);
+  const int share = n_s * (p.x_is_a ? p.m_tiles : p.n_tiles);
+  const int share_id = (p.pair ? s / 2 : s) * (p.x_is_a ? p.m_tiles : p.n_tiles) + (p.x_is_a ? mt : nt);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform roles
   if (warp == 0 && lane == 0) {
@@ -168,8 +174,12 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           }
         } else if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
-          for (int j = 0; j < nb_x; ++j)
-            ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], xc0 + 64 * j, x0 + s - 1, y0 - 1, n);
+          for (int j = 0; j < nb_x; ++j) {
+            // pair mode: box j = the same channels one kernel column further (the last pass repeats column 2: ignored rows)
+            const int cj = p.pair ? xc0 : xc0 + 64 * j;
+            const int sj = p.pair ? min(s + j, 2) : s;
+            ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], cj, x0 + sj - 1, y0 - 1, n);
+          }
           for (int j = 0; j < nb_z; ++j)
             ptx::tma_load_4d(st + z_off + j * WG_PLAIN_BLOCK, &map_z, &full_bar[stage], zc0 + 64 * j, x0, y0, n);
         }
@@ -274,7 +284,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (p_end > p_begin) {
       ptx::mbar_wait(done_bar, 0);
       ptx::tc_fence_after();
-      const bool row_ok = (m0 + row) < p.Mtot && p.debug != 1;
+      const bool row_ok = (p.pair ? (s + (row >> 6)) < 3 : (m0 + row) < p.Mtot) && p.debug != 1;
       // the splits of one tile finish together and add into the same addresses: start each at a different
       // (kernel row, column block) so that concurrent reductions mostly hit different L2 lines
       const int rot = p.debug == 2 ? 0 : split;
@@ -306,8 +316,9 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       } else
       for (int rr = 0; rr < 3; ++rr) {
         const int r = (rr + rot) % 3;
-        const int tap = r * 3 + s;
-        float* dst = p.ws + ((long long)tap * p.Mtot + (m0 + row)) * p.Ntot + n0;
+        const int tap = r * 3 + s + (p.pair ? (row >> 6) : 0);
+        const int mrow = p.pair ? (row & 63) : m0 + row;
+        float* dst = p.ws + ((long long)tap * p.Mtot + mrow) * p.Ntot + n0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * p.n_cols;
 #pragma unroll 1
         for (int cb = 0; cb < n_cb; ++cb) {
@@ -416,7 +427,8 @@ extern "C" {
 size_t fosvos_conv3x3_wgrad_tc_workspace_bytes(int CinP, int CoutP) { return (size_t)9 * CinP * CoutP * sizeof(float); }
 
 // orientation: put the wider channel dimension on M (=128 rows); tiny couts (side_prep) go to N
-static inline int wg_x_is_a(int CinP, int CoutP) { return (CoutP < 64 || (CinP >= 128 && CoutP < 128)) ? 1 : 0; }
+// (Cin = Cout = 64 goes to the X-on-M orientation for its two-columns-per-pass mode)
+static inline int wg_x_is_a(int CinP, int CoutP) { return (CoutP < 64 || (CinP >= 128 && CoutP < 128) || (CinP == 64 && CoutP == 64)) ? 1 : 0; }
 
 int fosvos_conv3x3_wgrad_tc_orientation(int CinP, int CoutP) { return wg_x_is_a(CinP, CoutP); }
 
@@ -437,6 +449,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   p.Mtot = p.x_is_a ? CinP : CoutP;
   p.Ntot = p.x_is_a ? CoutP : CinP;
   p.c8 = (CinP == 8 && !p.x_is_a && !getenv("FOSVOS_WG_NO_C8")) ? 1 : 0;
+  p.pair = (p.x_is_a && CinP == 64) ? 1 : 0;
   p.c8_lbo = WG_C8_ROW; p.c8_sbo = 16;
   p.n_cols = p.c8 ? 32 : p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
   p.nb_n = (p.n_cols + 63) / 64;
@@ -465,7 +478,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   // Split-K over pixel ranges.  Every CTA ends with 3 * 128 * n_cols fp32 reductions into the workspace, so the
   // split count trades tensor-core occupancy against reduction traffic: fill the machine once; go to a second
   // wave only while each CTA still has enough patches to amortise its epilogue.
-  const int items = p.m_tiles * p.n_tiles * (p.c8 ? 1 : 3);
+  const int items = p.m_tiles * p.n_tiles * (p.c8 ? 1 : p.pair ? 2 : 3);
   int splits = max(1, num_sms() / items);
   if ((long long)p.patches >= 16LL * 2 * num_sms() / items) splits = max(1, (2 * num_sms()) / items);
   if (const char* e = getenv("FOSVOS_WG_SPLITS")) { const int v = atoi(e); if (v > 0) splits = v; }

@@ -355,7 +355,7 @@ def test_fused_window_equals_sequential_micro_iterations(precision):
     for fuse in (False, True):
         net = _net(sd, precision)
         tr = OnlineTrainer(net, H, W, n, FB.get_optimizer_online(net, learning_rate=1e-6), use_graph=True, fuse_window=fuse)
-        losses = []
+        losses, after_first = [], None
         for step in range(2):
             if fuse:
                 tr.set_frames(frames.to(DEV), masks.to(DEV))
@@ -364,10 +364,15 @@ def test_fused_window_equals_sequential_micro_iterations(precision):
                 for i in range(n):
                     tr.set_frame(frames[i:i + 1].to(DEV), masks[i:i + 1].to(DEV))
                     tr.run(1, losses)
-        results.append((losses, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}))
+            if step == 0:
+                after_first = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+        results.append((losses, after_first))
     (l0, w0), (l1, w1) = results
     assert len(l0) == len(l1) == 2 * n
     assert np.allclose(l0, l1, rtol=1e-5 if precision == "fp32" else 2e-2), (l0, l1)
+    # weights are compared after the FIRST step: from the second window on, the 1e-5-level differences of the atomic
+    # summation order can flip the ReLU mask of a borderline activation of the 3x5 last stage (seen in BOTH schedules,
+    # run to run), which moves single weight-gradient entries by percents -- chaos of the test case, not of the schedule
     for k in ["stages.0.0.weight", "stages.1.3.weight", "stages.4.5.weight", "stages.3.1.bias", "side_prep.0.weight", "fuse.weight"]:
         d0, d1 = w0[k] - sd[k], w1[k] - sd[k]
         # (cancelling sums over noise frames: the fp32 summation ORDER differs between the two schedules)
