@@ -96,6 +96,7 @@ struct TcParams {
   int k_chunks;                  // ceil(CinP / 64)
   int cin_pad;                   // k_chunks * 64: per-tap K extent of the packed weight
   int taps;                      // 9 (3x3, pad 1) or 1 (1x1)
+  uint32_t dn_mul, dn_shift, dx_mul, dx_shift, dy_mul, dy_shift;   // fast division by n_tiles_n, tiles_x, tiles_y
   int halo_bytes;                // MODE_HALO: (TH+2) * TW * 128
   int flags;
 };
@@ -195,11 +196,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint32_t b_dst = btiles_a, bbar_full = bfull_a, bbar_empty = bempty_a;
     (void)bstage; (void)bphase; (void)b_dst; (void)bbar_full; (void)bbar_empty;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles_n;
-      int m = tile / p.n_tiles_n;
-      const int tx = m % p.tiles_x; m /= p.tiles_x;
-      const int ty = m % p.tiles_y;
-      const int n = m / p.tiles_y;
+      // tile -> (n-tile, patch x, patch y, frame) with multiply-shift divisions (three real divisions per tile and
+      // thread were ~45 % of the epilogue's instructions)
+      int m = (int)ptx::fast_div((uint32_t)tile, p.dn_mul, p.dn_shift);
+      const int nt = tile - m * p.n_tiles_n;
+      int m2 = (int)ptx::fast_div((uint32_t)m, p.dx_mul, p.dx_shift);
+      const int tx = m - m2 * p.tiles_x;
+      const int n = (int)ptx::fast_div((uint32_t)m2, p.dy_mul, p.dy_shift);
+      const int ty = m2 - n * p.tiles_y;
       const int x0 = tx * TW, y0 = ty * TH, n0 = nt * BN;
       if constexpr (MODE == MODE_C8) {
         ptx::mbar_wait_a(bar_empty, phase ^ 1);
@@ -372,24 +376,47 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
     constexpr int GRP_THREADS = 32 * TC_EPI_WARPS / 2;
     uint8_t* buf = staging + grp * TC_SLAB_BYTES;
+    const uint32_t buf_a = ptx::smem_u32(buf);
     const int as = grp;
     const bool relu = (p.flags & FOSVOS_CONV_RELU) != 0;
+    const uint32_t bias_a = ptx::smem_u32(bias_s);
+    constexpr int MASK_PER_THREAD = TC_BM / (GRP_THREADS / 8);       // 16-byte mask chunks per thread and slab
+    const int tg = threadIdx.x - 64 - grp * GRP_THREADS;            // thread index inside the epilogue group
+    uint4 mk[MASK_PER_THREAD];
     // MASK alone (the data gradient) is applied to the staged slab with coalesced loads, see below; the register
     // path handles it only together with ACCUMULATE (one rounding of mask(acc) + old)
     const bool post = (p.flags & (FOSVOS_CONV_ACCUMULATE | TC_FLAG_MASK_IN_REGS)) != 0;
     const bool mask_slab = Cfg::STAGED && (p.flags & FOSVOS_CONV_MASK) && !post;
     int it = grp;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
-      const int nt = tile % p.n_tiles_n;
-      int m = tile / p.n_tiles_n;
-      const int tx = m % p.tiles_x; m /= p.tiles_x;
-      const int ty = m % p.tiles_y;
-      const int n = m / p.tiles_y;
+      // tile -> (n-tile, patch x, patch y, frame) with multiply-shift divisions (three real divisions per tile and
+      // thread were ~45 % of the epilogue's instructions)
+      int m = (int)ptx::fast_div((uint32_t)tile, p.dn_mul, p.dn_shift);
+      const int nt = tile - m * p.n_tiles_n;
+      int m2 = (int)ptx::fast_div((uint32_t)m, p.dx_mul, p.dx_shift);
+      const int tx = m - m2 * p.tiles_x;
+      const int n = (int)ptx::fast_div((uint32_t)m2, p.dy_mul, p.dy_shift);
+      const int ty = m2 - n * p.tiles_y;
       const int x0 = tx * TW, y0 = ty * TH;
       const int gx = x0 + px, gy = y0 + py, n0 = nt * BN;
       const bool in_img = gx < p.W && gy < p.H;
       const long long pix = ((long long)n * p.H + gy) * p.W + gx;
       const uint32_t aphase = (it >> 1) & 1;
+      // ReLU-backward mask (= the layer input's post-ReLU activation; x != 0 <=> x > 0) of the tile's first slab: thread ->
+      // (16-byte chunk tg & 7, pixel rows tg >> 3, + 32, ...), so a warp reads four pixels x 128 contiguous bytes.  Issued
+      // BEFORE the wait for the accumulator: the loads fly while the tensor cores still work on this tile.
+      auto load_mask = [&](int co_slab) {
+#pragma unroll
+        for (int jj = 0; jj < MASK_PER_THREAD; ++jj) {
+          const int rw = (tg >> 3) + jj * (GRP_THREADS / 8);
+          const int my = y0 + (rw >> p.tw_shift), mx = x0 + (rw & (TW - 1));
+          const int co = co_slab + 8 * (tg & 7);
+          mk[jj] = (mx < p.W && my < p.H && co < p.CoutP)
+                       ? __ldg(reinterpret_cast<const uint4*>(p.mask + (((long long)n * p.H + my) * p.W + mx) * p.CoutP + co))
+                       : make_uint4(~0u, ~0u, ~0u, ~0u);          // clipped by the TMA store anyway
+        }
+      };
+      if (mask_slab) load_mask(n0);
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
@@ -410,12 +437,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             for (int h = 0; h < 4; ++h) {
               const int co = co0 + 32 * half + 8 * h;    // < 512: bias_s holds zeros past CoutP
               float v[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + co + 4);
-              v[0] = __uint_as_float(r[8 * h]) + b0.x; v[1] = __uint_as_float(r[8 * h + 1]) + b0.y;
-              v[2] = __uint_as_float(r[8 * h + 2]) + b0.z; v[3] = __uint_as_float(r[8 * h + 3]) + b0.w;
-              v[4] = __uint_as_float(r[8 * h + 4]) + b1.x; v[5] = __uint_as_float(r[8 * h + 5]) + b1.y;
-              v[6] = __uint_as_float(r[8 * h + 6]) + b1.z; v[7] = __uint_as_float(r[8 * h + 7]) + b1.w;
+              const uint4 b0 = ptx::lds128(bias_a + 4 * co), b1 = ptx::lds128(bias_a + 4 * co + 16);
+              v[0] = __uint_as_float(r[8 * h]) + __uint_as_float(b0.x); v[1] = __uint_as_float(r[8 * h + 1]) + __uint_as_float(b0.y);
+              v[2] = __uint_as_float(r[8 * h + 2]) + __uint_as_float(b0.z); v[3] = __uint_as_float(r[8 * h + 3]) + __uint_as_float(b0.w);
+              v[4] = __uint_as_float(r[8 * h + 4]) + __uint_as_float(b1.x); v[5] = __uint_as_float(r[8 * h + 5]) + __uint_as_float(b1.y);
+              v[6] = __uint_as_float(r[8 * h + 6]) + __uint_as_float(b1.z); v[7] = __uint_as_float(r[8 * h + 7]) + __uint_as_float(b1.w);
               if (post) {
                 if (relu) {
 #pragma unroll
@@ -479,31 +505,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           if (live) {
             if (issuer) ptx::tma_store_wait_read<0>();    // the previous store of this group has read the buffer
             ptx::named_bar_sync(bar_a, GRP_THREADS);
-            uint8_t* rowp = buf + row * 128;
+            const uint32_t rowp = buf_a + row * 128;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<uint4*>(rowp + (((4 * half + c) ^ (row & 7)) << 4)) =
-                  make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+              ptx::sts128(rowp + (((4 * half + c) ^ (row & 7)) << 4),
+                          make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]));
             if (mask_slab) {
-              // ReLU backward on the staged slab: thread -> (16-byte chunk c, pixel rows rw, rw + 32, ...), so a warp reads
-              // four pixels x 128 contiguous bytes of the mask (= the layer input's post-ReLU activation): x != 0 <=> x > 0
+              // ReLU backward on the staged slab with the mask chunks fetched ahead (see load_mask)
               ptx::named_bar_sync(bar_a, GRP_THREADS);
-              const int tg = threadIdx.x - 64 - grp * GRP_THREADS;
-              const int c = tg & 7;
-              if (co0 + 8 * c < p.CoutP) {
 #pragma unroll
-                for (int jj = 0; jj < TC_BM / (GRP_THREADS / 8); ++jj) {
-                  const int rw = (tg >> 3) + jj * (GRP_THREADS / 8);
-                  const int my = y0 + (rw >> p.tw_shift), mx = x0 + (rw & (TW - 1));
-                  if (mx < p.W && my < p.H) {
-                    const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.mask + (((long long)n * p.H + my) * p.W + mx) * p.CoutP + co0 + 8 * c));
-                    uint4* sp = reinterpret_cast<uint4*>(buf + rw * 128 + ((c ^ (rw & 7)) << 4));
-                    uint4 v = *sp;
-                    v.x &= __vcmpne2(mk.x, 0u); v.y &= __vcmpne2(mk.y, 0u); v.z &= __vcmpne2(mk.z, 0u); v.w &= __vcmpne2(mk.w, 0u);
-                    *sp = v;
-                  }
-                }
+              for (int jj = 0; jj < MASK_PER_THREAD; ++jj) {
+                const int rw = (tg >> 3) + jj * (GRP_THREADS / 8);
+                const uint32_t sp = buf_a + rw * 128 + (((tg & 7) ^ (rw & 7)) << 4);
+                uint4 v = ptx::lds128(sp);
+                v.x &= __vcmpne2(mk[jj].x, 0u); v.y &= __vcmpne2(mk[jj].y, 0u); v.z &= __vcmpne2(mk[jj].z, 0u); v.w &= __vcmpne2(mk[jj].w, 0u);
+                ptx::sts128(sp, v);
               }
+              if (j + 1 < SLABS) load_mask(n0 + 64 * (j + 1));      // in flight during the next slab's TMEM load and math
             }
             ptx::fence_proxy_async_smem();
             ptx::named_bar_sync(bar_b, GRP_THREADS);
@@ -724,6 +742,17 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   if (const char* e = getenv("FOSVOS_TC_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && (v & (v - 1)) == 0) BN = v; }
   if (c8) BN = 64;
   p.n_tiles_n = ceil_div(Cout, BN);
+  {
+    auto fd = [](int d, uint32_t& mul, uint32_t& shift) {
+      uint32_t l = 0;
+      while ((1u << l) < (uint32_t)d) ++l;
+      mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - (uint64_t)d)) / (uint64_t)d + 1);
+      shift = l;
+    };
+    fd(p.n_tiles_n, p.dn_mul, p.dn_shift);
+    fd(p.tiles_x, p.dx_mul, p.dx_shift);
+    fd(p.tiles_y, p.dy_mul, p.dy_shift);
+  }
   FOSVOS_REQUIRE(m_tiles * p.n_tiles_n < (1LL << 31), "%s: too many tiles", what);
   p.total_tiles = (int)(m_tiles * p.n_tiles_n);
 

@@ -193,6 +193,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// explicit shared-space 16-byte accesses on a 32-bit shared address (pointers derived from the dynamic shared-memory base
+// by integer alignment arithmetic lose their address space: the compiler then emits slower generic LD/ST)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// n / d for 0 <= n < 2^31 with d's precomputed (mul, shift): q = (umulhi(mul, n) + n) >> shift
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shift) { return (__umulhi(mul, n) + n) >> shift; }
+
 // packed fp32 FMA (sm_100: two independent fused multiply-adds in one instruction): d = a * b + c, component-wise
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
