@@ -71,10 +71,14 @@ template <int BN, int MODE> struct TcCfg {
   static constexpr int B_BYTES = MODE == MODE_C8 ? 0 : BN * TC_BK * 2;
   // MODE_HALO: two rings -- STAGES halo boxes (A) followed by B_STAGES weight tiles (B); otherwise one ring of A+B
   static constexpr int STAGE_BYTES = MODE == MODE_HALO ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 3 : (BN >= 128) ? 4 : (BN >= 64) ? 5 : 6)
+  static constexpr int STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 3 : (BN >= 128) ? 4 : (BN >= 64) ? 4 : 6)
                                 : MODE == MODE_C8 ? 8 : (BN >= 256) ? 3 : (BN >= 128) ? 5 : (BN >= 64) ? 7 : 8;
-  static constexpr int B_STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 4 : (BN >= 128) ? 6 : 9) : 0;
-  static constexpr int RING_BYTES = STAGES * STAGE_BYTES + B_STAGES * B_BYTES;
+  // narrow tiles: one B stage = the three vertical taps of a kernel column (a N = 64 MMA is issue-bound at ~57 cycles, so
+  // a barrier round trip per four MMAs costs a third on top; twelve MMAs per wait bring it under 10 %)
+  static constexpr int B_GROUP = (MODE == MODE_HALO && BN <= 64) ? 3 : 1;
+  static constexpr int B_STAGE_BYTES = B_GROUP * B_BYTES;
+  static constexpr int B_STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 4 : (BN >= 128) ? 6 : 4) : 0;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES + B_STAGES * B_STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   // BN >= 64: each epilogue group stages 64-channel output slabs (128 px x 128 B, SWIZZLE_128B) for TMA stores
   static constexpr bool STAGED = BN >= 64;
@@ -229,18 +233,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             __syncwarp();
             a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_dst = tiles_a; bar_full = full_a; bar_empty = empty_a; }
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < 3; r += Cfg::B_GROUP) {
               ptx::mbar_wait_a(bbar_empty, bphase ^ 1);
               if (ptx::elect_one()) {
                 if (p.flags & TC_FLAG_SKIP_B) {
                   ptx::mbar_expect_tx_a(bbar_full, 0);
                 } else {
-                  ptx::mbar_expect_tx_a(bbar_full, Cfg::B_BYTES);
-                  ptx::tma_load_2d_a(b_dst, &map_w, bbar_full, (3 * r + s) * p.cin_pad + c, n0);
+                  ptx::mbar_expect_tx_a(bbar_full, Cfg::B_STAGE_BYTES);
+#pragma unroll
+                  for (int g = 0; g < Cfg::B_GROUP; ++g)
+                    ptx::tma_load_2d_a(b_dst + g * Cfg::B_BYTES, &map_w, bbar_full, (3 * (r + g) + s) * p.cin_pad + c, n0);
                 }
               }
               __syncwarp();
-              b_dst += Cfg::B_BYTES; bbar_full += 8; bbar_empty += 8;
+              b_dst += Cfg::B_STAGE_BYTES; bbar_full += 8; bbar_empty += 8;
               if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; b_dst = btiles_a; bbar_full = bfull_a; bbar_empty = bempty_a; }
             }
           }
@@ -320,23 +326,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         uint32_t acc = 0;
         for (int bx = 0; bx < n_boxes; ++bx) {
           ptx::mbar_wait_a(bar_full, phase);                // halo box has landed
-          for (int r = 0; r < 3; ++r) {
-            ptx::mbar_wait_a(bbar_full, bphase);            // weight tile of tap (r, s) has landed
+          for (int r = 0; r < 3; r += Cfg::B_GROUP) {
+            ptx::mbar_wait_a(bbar_full, bphase);            // weight tile(s) of tap(s) (r.., s) have landed
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) {
-                ptx::umma_bf16_lohi(tmem_d, a_lo + r * tap_step + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc | k);
+              for (int g = 0; g < Cfg::B_GROUP; ++g) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  ptx::umma_bf16_lohi(tmem_d, a_lo + (r + g) * tap_step + 2 * k, b_lo + g * (Cfg::B_BYTES >> 4) + 2 * k, desc_hi, idesc,
+                                      acc | g | k);
+                }
               }
               ptx::umma_commit_a(bbar_empty);
-              if (r == 2) {
+              if (r + Cfg::B_GROUP >= 3) {
                 ptx::umma_commit_a(bar_empty);
                 if (bx == n_boxes - 1) ptx::umma_commit_a(tfull);
               }
             }
             __syncwarp();
             acc = 1;
-            b_lo += Cfg::B_BYTES >> 4; bbar_full += 8; bbar_empty += 8;
+            b_lo += Cfg::B_STAGE_BYTES >> 4; bbar_full += 8; bbar_empty += 8;
             if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; b_lo = b_lo0; bbar_full = bfull_a; bbar_empty = bempty_a; }
           }
           a_lo += Cfg::STAGE_BYTES >> 4; bar_full += 8; bar_empty += 8;
