@@ -8,17 +8,18 @@
 
 namespace fosvos {
 
-template <typename T>
+// IDX = unsigned (32-bit index arithmetic: a 64-bit division costs ~100 instructions, three of them per thread were
+// more than the pooling itself) whenever the element count allows, long long otherwise.
+template <typename T, typename IDX>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int OH, int OW,
                                    long long total) {
-  const int groups = C / 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IDX groups = (IDX)(C / 8);
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < (IDX)total; i += (IDX)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
-    long long r = i / groups;
-    const int ox = (int)(r % OW); r /= OW;
-    const int oy = (int)(r % OH);
-    const long long n = r / OH;
+    IDX r = i / groups;
+    const int ox = (int)(r % (IDX)OW); r /= (IDX)OW;
+    const int oy = (int)(r % (IDX)OH);
+    const long long n = (long long)(r / (IDX)OH);
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = -CUDART_INF_F;
@@ -40,17 +41,16 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, i
 
 // Gradient goes to the FIRST maximum of the window in (row, col) scan order -- the index
 // max_pool2d_with_indices records (strict '>' comparison against a running maximum).
-template <typename T>
+template <typename T, typename IDX>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* add, T* dx, int H,
                                    int W, int C, int OH, int OW, long long total) {
-  const int groups = C / 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IDX groups = (IDX)(C / 8);
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < (IDX)total; i += (IDX)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
-    long long r = i / groups;
-    const int ox = (int)(r % OW); r /= OW;
-    const int oy = (int)(r % OH);
-    const long long n = r / OH;
+    IDX r = i / groups;
+    const int ox = (int)(r % (IDX)OW); r /= (IDX)OW;
+    const int oy = (int)(r % (IDX)OH);
+    const long long n = (long long)(r / (IDX)OH);
     float v[4][8];
     float m[8];
     int arg[8];
@@ -99,7 +99,10 @@ int fosvos_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, in
   const long long total = (long long)N * OH * OW * (C / 8);
   const int blocks = (int)min((long long)num_sms() * 16, ceil_div_ll(total, 256));
   FOSVOS_DISPATCH_DTYPE(dtype, T, {
-    maxpool_fwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, H, W, C, OH, OW, total);
+    if (total + (long long)blocks * 256 < (1LL << 32))
+      maxpool_fwd_kernel<T, unsigned><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, H, W, C, OH, OW, total);
+    else
+      maxpool_fwd_kernel<T, long long><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, H, W, C, OH, OW, total);
   });
   return check_launch("maxpool2x2_fwd");
 }
@@ -116,7 +119,10 @@ int fosvos_maxpool2x2_bwd_add(const void* x, const void* dy, const void* add, vo
   const long long total = (long long)N * OH * OW * (C / 8);
   const int blocks = (int)min((long long)num_sms() * 16, ceil_div_ll(total, 256));
   FOSVOS_DISPATCH_DTYPE(dtype, T, {
-    maxpool_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)dy, (const T*)add, (T*)dx, H, W, C, OH, OW, total);
+    if (total + (long long)blocks * 256 < (1LL << 32))
+      maxpool_bwd_kernel<T, unsigned><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)dy, (const T*)add, (T*)dx, H, W, C, OH, OW, total);
+    else
+      maxpool_bwd_kernel<T, long long><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)dy, (const T*)add, (T*)dx, H, W, C, OH, OW, total);
   });
   return check_launch("maxpool2x2_bwd");
 }
