@@ -308,11 +308,11 @@ def conv_roofline(net, frames, peaks, precision):
     peak = peaks["bf16_tflops"]
     # DRAM bytes of the same 17 launches from the committed ncu --set full capture (only if it was taken at this batch)
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01g_conv_forward_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r01h_conv_forward_traffic.json")
     if impl == "tc" and os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("batch") == n:
-            traffic, traffic_src = tj["traffic_bytes"], "profiles/r01g_conv_forward_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the 17 launches of one batch-%d forward)" % n
+            traffic, traffic_src = tj["traffic_bytes"], "profiles/r01h_conv_forward_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the 17 launches of one batch-%d forward)" % n
     return dict(bound="tensor", kernel="conv3x3_tc_kernel (17 launches = one forward pass)" if impl == "tc" else "conv3x3_simt_kernel",
                 achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
                 peak_source=peaks["source"] + " burst", batch=n, ms_per_forward_convs=ms, per_layer=per_layer)
