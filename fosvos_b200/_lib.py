@@ -62,6 +62,7 @@ SIGNATURES = {
     "fosvos_bal_loss_stats_bytes": (C.c_size_t, []),
     "fosvos_bal_loss_fwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp]),
     "fosvos_bal_loss_fwd_bwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _f, _vp, _vp]),
+    "fosvos_bal_loss_fwd_bwd_frames": (_i, [_vp, _vp, _ll, _i, _i, _vp, _ll, _vp, _vp, _f, _vp, _vp]),
     "fosvos_bal_loss_bwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _f, _vp, _vp]),
     "fosvos_sgd_chunk_elems": (_i, []),
     "fosvos_sgd_step": (_i, [_vp, _i, _vp, _i, _f, _i, _vp]),

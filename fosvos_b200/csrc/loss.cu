@@ -106,7 +106,10 @@ bal_loss_fwd_kernel(const float* __restrict__ out, const float* __restrict__ lab
 __global__ void __launch_bounds__(LOSS_THREADS)
 bal_loss_fused_kernel(const float* __restrict__ out, const float* __restrict__ lab, long long n, int size_average,
                       double* __restrict__ stats, float* __restrict__ loss, const float* __restrict__ grad_out, float grad_scale,
-                      float* __restrict__ dx) {
+                      float* __restrict__ dx, long long stats_stride) {
+  // blockIdx.y = frame: every frame has its own label statistics, partial-sum slots and loss scalar
+  out += blockIdx.y * n; lab += blockIdx.y * n; dx += blockIdx.y * n;
+  stats += blockIdx.y * stats_stride; loss += blockIdx.y;
   const float tot = (float)n;
   float g = grad_scale * (grad_out ? *grad_out : 1.f);
   if (size_average) g /= tot;
@@ -229,8 +232,22 @@ int fosvos_bal_loss_fwd_bwd(const float* output, const float* label, long long n
                             float* loss, const float* grad_out, float grad_scale, float* dx, fosvos_stream_t stream) {
   FOSVOS_REQUIRE(output && label && stats && loss && dx && numel > 0, "bal_loss_fwd_bwd: bad arguments");
   bal_loss_fused_kernel<<<loss_blocks(numel), LOSS_THREADS, 0, as_stream(stream)>>>(output, label, numel, size_average, stats, loss,
-                                                                                   grad_out, grad_scale, dx);
+                                                                                   grad_out, grad_scale, dx, 0);
   return check_launch("bal_loss_fwd_bwd");
+}
+
+int fosvos_bal_loss_fwd_bwd_frames(const float* output, const float* label, long long numel_per_frame, int n_frames, int size_average,
+                                   double* stats, long long stats_stride, float* loss, const float* grad_out, float grad_scale,
+                                   float* dx, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(output && label && stats && loss && dx && numel_per_frame > 0 && n_frames > 0 && n_frames <= 65535,
+                 "bal_loss_fwd_bwd_frames: bad arguments");
+  FOSVOS_REQUIRE(stats_stride * (long long)sizeof(double) >= (long long)fosvos_bal_loss_stats_bytes(),
+                 "bal_loss_fwd_bwd_frames: stats stride smaller than fosvos_bal_loss_stats_bytes()");
+  const int per_frame = max(1, min(loss_blocks(numel_per_frame), ceil_div(num_sms(), n_frames)));
+  dim3 grid(per_frame, n_frames);
+  bal_loss_fused_kernel<<<grid, LOSS_THREADS, 0, as_stream(stream)>>>(output, label, numel_per_frame, size_average, stats, loss, grad_out,
+                                                                     grad_scale, dx, stats_stride);
+  return check_launch("bal_loss_fwd_bwd_frames");
 }
 
 int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel, int size_average,

@@ -183,18 +183,14 @@ class OnlineTrainer:
         n = self.frames.shape[0]
         outs, _, _, saved = net._run_forward(self.frames, save=True)
         douts: List[Optional[torch.Tensor]] = [None] * 5
-        maps = [4] if self.deep_w is None else [4, 0, 1, 2, 3]
-        for j in maps:
-            douts[j] = torch.empty_like(outs[j])
-        for i in range(n):
-            # the class-balanced loss normalises by the label counts of ITS frame (osvos_layers.py:26-39): per-frame calls
-            total = None
-            for j in maps:
-                w = None if j == 4 else self.deep_w
-                lj, _ = ops.bal_loss_fwd_bwd(outs[j][i:i + 1], self.masks[i:i + 1], False, self.loss_stats_all[i], w, self.scale,
-                                             out=douts[j][i:i + 1])
-                total = lj if total is None else total + self.deep_w * lj
-            self.window_losses[i].copy_(total)
+        # the class-balanced loss normalises by the label counts of ITS frame (osvos_layers.py:26-39): one launch per
+        # output map computes every frame's loss and gradient with that frame's statistics
+        _, douts[4] = ops.bal_loss_fwd_bwd_frames(outs[4], self.masks, False, self.loss_stats_all, None, self.scale,
+                                                  losses=self.window_losses)
+        if self.deep_w is not None:
+            for j in range(4):
+                lj, douts[j] = ops.bal_loss_fwd_bwd_frames(outs[j], self.masks, False, self.loss_stats_all, self.deep_w, self.scale)
+                self.window_losses.add_(self.deep_w * lj)
         self.last_loss.copy_(self.window_losses[n - 1])
         self.loss_sum.add_(self.window_losses.sum())
         net._run_backward(saved, douts, self.grads, self.wgrad_ws)

@@ -270,6 +270,25 @@ def bal_loss_fwd_bwd(output: torch.Tensor, label: torch.Tensor, size_average: bo
     return loss, dx
 
 
+def bal_loss_fwd_bwd_frames(output: torch.Tensor, label: torch.Tensor, size_average: bool, stats: torch.Tensor,
+                            grad_out: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                            out: Optional[torch.Tensor] = None, losses: Optional[torch.Tensor] = None):
+    """Per-frame loss and gradient of a batch (N,1,H,W) in ONE launch; ``stats`` (N, S) float64 holds every frame's
+    label statistics (from per-frame ``bal_loss_fwd`` calls).  -> (losses (N,) fp32, dx)"""
+    L.require_device(output.device)
+    assert output.dtype == torch.float32 and label.dtype == torch.float32 and output.shape == label.shape
+    output, label = output.contiguous(), label.contiguous()
+    n = output.shape[0]
+    assert stats.dtype == torch.float64 and stats.dim() == 2 and stats.shape[0] == n and stats.is_contiguous()
+    dx = torch.empty_like(output) if out is None else out
+    if losses is None:
+        losses = torch.empty(n, dtype=torch.float32, device=output.device)
+    L.check(L.lib().fosvos_bal_loss_fwd_bwd_frames(output.data_ptr(), label.data_ptr(), output.numel() // n, n, int(size_average),
+                                                   stats.data_ptr(), stats.shape[1], losses.data_ptr(), L.ptr(grad_out), float(grad_scale),
+                                                   dx.data_ptr(), L.stream()), "bal_loss_fwd_bwd_frames")
+    return losses, dx
+
+
 def bal_loss_bwd(output: torch.Tensor, label: torch.Tensor, size_average: bool, stats: torch.Tensor,
                  grad_out: Optional[torch.Tensor], grad_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     output, label = output.contiguous(), label.contiguous()

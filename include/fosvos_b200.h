@@ -220,6 +220,13 @@ int fosvos_bal_loss_fwd(const float* output, const float* label, long long numel
 int fosvos_bal_loss_fwd_bwd(const float* output, const float* label, long long numel, int size_average,
                             double* stats, float* loss, const float* grad_out, float grad_scale,
                             float* dx, fosvos_stream_t stream);
+/* The same for n_frames maps in one launch, each frame with ITS OWN label statistics (the class balance is per
+ * frame, osvos_layers.py:26-39): frame f uses output/label/dx + f*numel_per_frame, stats + f*stats_stride
+ * (doubles) and loss[f]. */
+int fosvos_bal_loss_fwd_bwd_frames(const float* output, const float* label, long long numel_per_frame,
+                                   int n_frames, int size_average, double* stats, long long stats_stride,
+                                   float* loss, const float* grad_out, float grad_scale, float* dx,
+                                   fosvos_stream_t stream);
 int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel, int size_average,
                         const double* stats, const float* grad_out, float grad_scale, float* dx,
                         fosvos_stream_t stream);
