@@ -70,9 +70,12 @@ template <int BN, int MODE> struct TcCfg {
   static constexpr int A_BYTES = MODE == MODE_C8 ? C8_A_BYTES : MODE == MODE_HALO ? HALO_A_BYTES : TC_A_BYTES;
   static constexpr int B_BYTES = MODE == MODE_C8 ? 0 : BN * TC_BK * 2;
   // MODE_HALO: two rings -- STAGES halo boxes (A) followed by B_STAGES weight tiles (B); otherwise one ring of A+B
-  static constexpr int STAGE_BYTES = MODE == MODE_HALO ? A_BYTES : A_BYTES + B_BYTES;
+  // generic narrow tiles (side_prep, N = 16/32): two 64-channel K blocks per stage -- the MMAs are issue-bound (~57 cycles
+  // each), a barrier round trip per four of them is a measurable tax
+  static constexpr int K_GROUP = (MODE == MODE_GENERIC && BN <= 32) ? 2 : 1;
+  static constexpr int STAGE_BYTES = MODE == MODE_HALO ? A_BYTES : K_GROUP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 3 : (BN >= 128) ? 4 : (BN >= 64) ? 4 : 6)
-                                : MODE == MODE_C8 ? 8 : (BN >= 256) ? 3 : (BN >= 128) ? 5 : (BN >= 64) ? 7 : 8;
+                                : MODE == MODE_C8 ? 8 : (BN >= 256) ? 3 : (BN >= 128) ? 5 : (BN >= 64) ? 7 : 5;
   // narrow tiles: one B stage = the three vertical taps of a kernel column (a N = 64 MMA is issue-bound at ~57 cycles, so
   // a barrier round trip per four MMAs costs a third on top; twelve MMAs per wait bring it under 10 %)
   static constexpr int B_GROUP = (MODE == MODE_HALO && BN <= 64) ? 3 : 1;
@@ -259,12 +262,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           const int yy = p.taps == 9 ? y0 + r - 1 : y0;
           for (int s = 0; s < n_r; ++s) {
             const int xx = p.taps == 9 ? x0 + s - 1 : x0;
-            for (int c = 0; c < p.cin_pad; c += TC_BK, wk += TC_BK) {
+            for (int c = 0; c < p.cin_pad; c += Cfg::K_GROUP * TC_BK, wk += Cfg::K_GROUP * TC_BK) {
               ptx::mbar_wait_a(bar_empty, phase ^ 1);
               if (ptx::elect_one()) {
-                ptx::mbar_expect_tx_a(bar_full, Cfg::STAGE_BYTES);
-                ptx::tma_load_4d_a(a_dst, &map_x, bar_full, c, xx, yy, n);
-                ptx::tma_load_2d_a(a_dst + Cfg::A_BYTES, &map_w, bar_full, wk, n0);
+                const int ng = min(Cfg::K_GROUP, (p.cin_pad - c) / TC_BK);        // K blocks in this stage (the last may be short)
+                ptx::mbar_expect_tx_a(bar_full, ng * (Cfg::A_BYTES + Cfg::B_BYTES));
+#pragma unroll
+                for (int g = 0; g < Cfg::K_GROUP; ++g) {
+                  if (g < ng) {
+                    ptx::tma_load_4d_a(a_dst + g * (Cfg::A_BYTES + Cfg::B_BYTES), &map_x, bar_full, c + g * TC_BK, xx, yy, n);
+                    ptx::tma_load_2d_a(a_dst + g * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::A_BYTES, &map_w, bar_full, wk + g * TC_BK, n0);
+                  }
+                }
               }
               __syncwarp();
               a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
@@ -354,18 +363,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         }
       } else {
         const uint32_t tfull = ptx::smem_u32(&tmem_full[as]);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int stages_per_tap = (p.k_chunks + Cfg::K_GROUP - 1) / Cfg::K_GROUP;
+        const int n_st = p.taps * stages_per_tap;
+        for (int kb = 0, in_tap = 0; kb < n_st; ++kb) {
           ptx::mbar_wait_a(bar_full, phase);              // TMA bytes have landed
           ptx::tc_fence_after();
+          const int ng = min(Cfg::K_GROUP, p.k_chunks - in_tap * Cfg::K_GROUP);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-              ptx::umma_bf16_lohi(tmem_d, a_lo + 2 * k, a_lo + (Cfg::A_BYTES >> 4) + 2 * k, desc_hi, idesc, (kb | k) != 0);
+            for (int g = 0; g < Cfg::K_GROUP; ++g) {
+              if (g < ng) {
+                const uint32_t a_g = a_lo + g * ((Cfg::A_BYTES + Cfg::B_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+                  ptx::umma_bf16_lohi(tmem_d, a_g + 2 * k, a_g + (Cfg::A_BYTES >> 4) + 2 * k, desc_hi, idesc, (kb | g | k) != 0);
+                }
+              }
             }
             ptx::umma_commit_a(bar_empty);                // frees the smem slot when the MMAs retire
-            if (kb == num_kb - 1) ptx::umma_commit_a(tfull);   // accumulator complete -> epilogue
+            if (kb == n_st - 1) ptx::umma_commit_a(tfull);     // accumulator complete -> epilogue
           }
+          if (++in_tap == stages_per_tap) in_tap = 0;
           __syncwarp();
           a_lo += Cfg::STAGE_BYTES >> 4; bar_full += 8; bar_empty += 8;
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; bar_full = full_a; bar_empty = empty_a; }
