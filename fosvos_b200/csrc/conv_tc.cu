@@ -187,7 +187,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_kb = p.taps * p.k_chunks;
   const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
 
   if (warp == 0) {
@@ -262,10 +261,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           const int yy = p.taps == 9 ? y0 + r - 1 : y0;
           for (int s = 0; s < n_r; ++s) {
             const int xx = p.taps == 9 ? x0 + s - 1 : x0;
-            for (int c = 0; c < p.cin_pad; c += Cfg::K_GROUP * TC_BK, wk += Cfg::K_GROUP * TC_BK) {
+            for (int c = 0; c < p.cin_pad; c += Cfg::K_GROUP * TC_BK) {
+              const int ng = min(Cfg::K_GROUP, (p.cin_pad - c) / TC_BK);          // K blocks in this stage (the last may be short)
               ptx::mbar_wait_a(bar_empty, phase ^ 1);
               if (ptx::elect_one()) {
-                const int ng = min(Cfg::K_GROUP, (p.cin_pad - c) / TC_BK);        // K blocks in this stage (the last may be short)
                 ptx::mbar_expect_tx_a(bar_full, ng * (Cfg::A_BYTES + Cfg::B_BYTES));
 #pragma unroll
                 for (int g = 0; g < Cfg::K_GROUP; ++g) {
@@ -276,6 +275,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 }
               }
               __syncwarp();
+              wk += ng * TC_BK;
               a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
               if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_dst = tiles_a; bar_full = full_a; bar_empty = empty_a; }
             }

@@ -206,6 +206,13 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 // n / d for 0 <= n < 2^31 with d's precomputed (mul, shift): q = (umulhi(mul, n) + n) >> shift
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shift) { return (__umulhi(mul, n) + n) >> shift; }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS: no register, no scoreboard); !valid writes zeros and reads nothing
+__device__ __forceinline__ void cp_async_8_zfill(uint32_t dst, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // packed fp32 FMA (sm_100: two independent fused multiply-adds in one instruction): d = a * b + c, component-wise
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;

@@ -183,6 +183,8 @@ int fosvos_side_prepare(const float* const* upscale_w /*4: (16,16,k,k)*/,
  * prob (fp32) / mask (uint8) of the fused map: optional, NULL to skip.
  * general=0: fast path, valid when fosvos_side_check_diagonal reports 0 violations; needs a
  *            workspace of fosvos_side_workspace_bytes(h,w,N) bytes (low-res head maps).
+ * general=2: the same for up-sampling kernels that factor exactly into a column and a row
+ *            vector (params[fosvos_side_params_separable_flag()] == 0): two FMAs per stage and pixel.
  * general=1: exact for arbitrary upscale weights (16x more arithmetic), workspace unused. */
 size_t fosvos_side_workspace_bytes(const int* h /*4*/, const int* w /*4*/, int N);
 int fosvos_side_fwd(const void* const* sp /*4*/, const int* h /*4*/, const int* w /*4*/,

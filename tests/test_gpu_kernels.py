@@ -71,6 +71,10 @@ CONV_CASES = [
     (1, 8, 40, 128, 16),
     (1, 30, 54, 24, 40),
     (1, 5, 3, 256, 256),
+    # narrow-N tiles take two 64-channel K blocks per pipeline stage: odd block counts end on a short stage
+    (1, 12, 20, 64, 16),
+    (1, 10, 18, 192, 32),
+    (2, 14, 9, 32, 32),
 ]
 
 
@@ -307,7 +311,7 @@ def _side_params(sd):
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("general", [False, True, 2])
-@pytest.mark.parametrize("HW", [(48, 72), (45, 70), (33, 17)])
+@pytest.mark.parametrize("HW", [(48, 72), (45, 70), (33, 17), (70, 1100)])
 def test_side_chain_forward(dt, general, HW):
     H, W = HW
     sp, sd = _side_inputs(2, H, W, 11, dt)
