@@ -331,8 +331,15 @@ def side_roofline(net, frames, peaks):
     low = sum(t.shape[1] * t.shape[2] for t in sps)
     bytes_per_frame = 16 * low * esz + 5 * H * W * 4 + H * W * 4 + H * W       # read sp; write 5 maps + prob + mask
     achieved = bytes_per_frame * n / (ms / 1e3) / 1e9
+    # DRAM bytes of the two launches from the committed ncu --set full capture (only if it was taken at this batch)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01i_side_traffic.json")
+    if mode == 2 and W % 2 == 0 and esz == 2 and os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("batch") == n:
+            traffic = tj["traffic_bytes"]
     return dict(bound="hbm", kernel="side_heads2_kernel + " + ("side_upsample_sep2_kernel" if mode == 2 and W % 2 == 0 else "side_upsample_sep_kernel" if mode == 2 else "side_upsample_kernel"), achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
-                frac=achieved / peaks["hbm_gbs"], traffic=None, batch=n, ms=ms, bytes_per_frame=bytes_per_frame)
+                frac=achieved / peaks["hbm_gbs"], traffic=traffic, batch=n, ms=ms, bytes_per_frame=bytes_per_frame)
 
 
 def loss_roofline(n, dev, peaks):
