@@ -54,6 +54,7 @@ SIGNATURES = {
     "fosvos_maxpool2x2_bwd_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_params_bytes": (C.c_size_t, []),
     "fosvos_side_workspace_bytes": (C.c_size_t, [_vp, _vp, _i]),
+    "fosvos_side_upsample_plan": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     "fosvos_side_prepare": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fosvos_side_check_diagonal": (_i, [_vp, _vp, _vp]),
     "fosvos_side_params_separable_flag": (_i, []),

@@ -187,6 +187,11 @@ int fosvos_side_prepare(const float* const* upscale_w /*4: (16,16,k,k)*/,
  *            vector (params[fosvos_side_params_separable_flag()] == 0): two FMAs per stage and pixel.
  * general=1: exact for arbitrary upscale weights (16x more arithmetic), workspace unused. */
 size_t fosvos_side_workspace_bytes(const int* h /*4*/, const int* w /*4*/, int N);
+/* Launch plan of the general=2 kernel for even W on a GPU with `num_sms` SMs: rows and pixel pairs per work item
+ * and the dynamic shared memory of a block (two staging buffers of low-res taps).  Host arithmetic only (no
+ * device needed): exposed so that the staging-window bounds can be checked on a CPU-only machine. */
+int fosvos_side_upsample_plan(int N, int H, int W, int num_sms, int* rows_per_item, int* pairs_per_item,
+                              int* smem_bytes);
 int fosvos_side_fwd(const void* const* sp /*4*/, const int* h /*4*/, const int* w /*4*/,
                     const void* params, float* const* out /*5*/, float* prob, uint8_t* mask,
                     void* workspace, int general, int N, int H, int W, int dtype,

@@ -34,6 +34,51 @@ def test_library_exports_every_declared_symbol():
     assert L.lib().fosvos_side_params_bytes() == 4 * (4 + 4 * 36 + 18 * (16 + 64 + 256 + 1024)) + 2 * 16 * (4 + 16 + 64 + 256) + 2 * 16 * 30 + 16
 
 
+@pytest.mark.parametrize("HW", [(480, 854), (240, 426), (384, 682), (48, 72), (45, 70), (70, 1100), (33, 18), (6, 2), (17, 2050)])
+def test_side_upsample_plan_keeps_every_tap_inside_its_staging_window(HW):
+    """The two-pixel separable up-sampling kernel (side.cu: side_upsample_sep2_kernel) reads the low-res taps of a
+    work item from a shared-memory window staged per stage.  The launch plan is host arithmetic exported through the
+    C ABI; the kernel's index formulas are restated here and checked exhaustively: every tap a pixel pair touches lies
+    inside the staged window, the window fits the plan's shared memory, the column blocks cover the frame."""
+    H, W = HW
+    hs, ws, h, w = [], [], H, W
+    for _ in range(4):
+        h, w = (h + 1) // 2, (w + 1) // 2            # ceil-mode 2x2 pools (osvos_vgg.py:90)
+        hs.append(h)
+        ws.append(w)
+    top = [((2 << i) * hs[i] + (2 << i) - H) // 2 for i in range(4)]      # center_crop offsets (osvos_layers.py:47-54)
+    left = [((2 << i) * ws[i] + (2 << i) - W) // 2 for i in range(4)]
+    for N, sms in ((1, 148), (5, 148), (16, 148), (3, 4)):
+        rows, ppi, smem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert L.lib().fosvos_side_upsample_plan(N, H, W, sms, ctypes.byref(rows), ctypes.byref(ppi), ctypes.byref(smem)) == 0
+        R, P = rows.value, ppi.value
+        pairs = W // 2
+        assert 1 <= R <= H and 1 <= P <= 256
+        xblocks = -(-pairs // P)
+        assert xblocks * P >= pairs
+        cw = [((2 * P - 1) >> (i + 1)) + 4 for i in range(4)]
+        rh = [((R - 1) >> (i + 1)) + 3 for i in range(4)]
+        assert smem.value == 2 * 8 * sum(c * r for c, r in zip(cw, rh)) <= 100 * 1024
+        for strip in range(-(-H // R)):
+            y0, y1 = strip * R, min(H, strip * R + R)
+            for i in range(4):
+                ro = ((y0 + top[i]) >> (i + 1)) - 1
+                lrs = [((y + top[i]) >> (i + 1)) - ro for y in range(y0, y1)]
+                assert min(lrs) - 1 >= 0 and max(lrs) <= rh[i] - 1, (N, strip, i)
+                assert ro + max(lrs) <= hs[i]            # row h is the zero row below the map, never further
+        for xb in range(xblocks):
+            x0 = 2 * xb * P
+            for i in range(4):
+                co = ((x0 + left[i]) >> (i + 1)) - 1
+                for t in range(P):
+                    if xb * P + t >= pairs:
+                        break
+                    c = ((x0 + 2 * t + left[i]) >> (i + 1)) - co
+                    assert c - 1 >= 0 and c + 1 <= cw[i] - 1, (N, xb, i, t)
+    bad = ctypes.c_int()
+    assert L.lib().fosvos_side_upsample_plan(1, 33, 17, 148, ctypes.byref(bad), ctypes.byref(bad), ctypes.byref(bad)) != 0     # odd width
+
+
 def test_no_cpu_fallback():
     net = FB.OSVOS_VGG(pretrained=0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
