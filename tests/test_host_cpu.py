@@ -182,6 +182,11 @@ def test_bench_sharding_two_ranks_gloo(tmp_path):
         "flat = torch.arange(6, dtype=torch.float32) * (rank + 1)\n"
         "allreduce_flat(flat)          # the data-parallel gradient exchange of offline training / distillation\n"
         "assert torch.equal(flat, torch.arange(6, dtype=torch.float32) * 3), flat\n"
+        "from fosvos_b200.sharding import allreduce_gradients\n"
+        "ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 300, 7, 2)]\n"
+        "for i, p in enumerate(ps[:3]): p.grad = torch.full_like(p, float((i + 1) * (rank + 1)))\n"
+        "allreduce_gradients(ps, bucket_bytes=1024)       # three gradients in two buckets, one parameter without a gradient\n"
+        "assert all(torch.equal(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(ps[:3])) and ps[3].grad is None\n"
         "open(os.path.join(os.path.dirname(__file__), f'rank{rank}.txt'), 'w').write(repr(mine))\n"
         "dist.destroy_process_group()\n")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
