@@ -289,7 +289,6 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       // (kernel row, column block) so that concurrent reductions mostly hit different L2 lines
       const int rot = p.debug == 2 ? 0 : split;
       const int n_cb = p.n_cols >> 4;
-#pragma unroll 1
       if (p.c8) {
         // accumulator r, column block sc = tap (r, sc), 8 channels each: ws[tap][cout][8]
 #pragma unroll 1
