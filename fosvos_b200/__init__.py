@@ -9,8 +9,8 @@ from .layers import (center_crop, class_balanced_cross_entropy_loss, interp_surg
                      upsample_filt)
 from .networks import OSVOS_VGG
 from .optim import FusedAdam, FusedSGD, get_optimizer_offline, get_optimizer_online
-from .online import finetune, infer_sequence, region_iou, sequences_for_rank
+from .online import finetune, finetune_samples, infer_sequence, region_iou, sequences_for_rank
 
 __all__ = ["OSVOS_VGG", "class_balanced_cross_entropy_loss", "center_crop", "upsample_filt", "interp_surgery",
-           "logit", "sigmoid_np", "mse_loss", "l1_loss", "FusedSGD", "FusedAdam", "get_optimizer_online", "get_optimizer_offline", "finetune",
+           "logit", "sigmoid_np", "mse_loss", "l1_loss", "FusedSGD", "FusedAdam", "get_optimizer_online", "get_optimizer_offline", "finetune", "finetune_samples",
            "infer_sequence", "region_iou", "sequences_for_rank"]

@@ -34,6 +34,8 @@ SIGNATURES = {
     "fosvos_conv3x3_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_tc_pool": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_conv3x3_side_tc_supported": (_i, [_i]),
+    "fosvos_conv3x3_side_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_simt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_tc_workspace_bytes": (C.c_size_t, [_i, _i]),
     "fosvos_conv3x3_wgrad_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -47,6 +49,8 @@ SIGNATURES = {
     "fosvos_adam_chunk_elems": (_i, []),
     "fosvos_adam_step": (_i, [_vp, _i, _vp, _i, C.c_float, C.c_float, C.c_float, _vp, _i, _vp]),
     "fosvos_pixel_loss": (_i, [_vp, _vp, C.c_longlong, _i, _i, C.c_float, _vp, _vp, _vp]),
+    "fosvos_relu_fwd": (_i, [_vp, _vp, _ll, _vp]),
+    "fosvos_relu_bwd": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "fosvos_taylor_rank": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _vp]),
     "fosvos_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -59,12 +63,16 @@ SIGNATURES = {
     "fosvos_side_check_diagonal": (_i, [_vp, _vp, _vp]),
     "fosvos_side_params_separable_flag": (_i, []),
     "fosvos_side_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_side_params_heads_offset": (_i, [_i]),
+    "fosvos_side_fwd_heads_done": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fosvos_side_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fosvos_bal_loss_stats_bytes": (C.c_size_t, []),
     "fosvos_bal_loss_fwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp]),
     "fosvos_bal_loss_fwd_bwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _f, _vp, _vp]),
     "fosvos_bal_loss_fwd_bwd_frames": (_i, [_vp, _vp, _ll, _i, _i, _vp, _ll, _vp, _vp, _f, _vp, _vp]),
     "fosvos_bal_loss_bwd": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _f, _vp, _vp]),
+    "fosvos_loss_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "fosvos_loss_window_finish": (_i, [_vp, _i, _vp, _vp, _vp]),
     "fosvos_sgd_chunk_elems": (_i, []),
     "fosvos_sgd_step": (_i, [_vp, _i, _vp, _i, _f, _i, _vp]),
     "fosvos_mask_iou": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
@@ -115,7 +123,36 @@ def require_device(device: torch.device) -> None:
 
 
 def stream() -> int:
+    """The current stream of the current device (the op wrappers make the tensors' device current first)."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _first_cuda_device(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (list, tuple)):
+            for b in a:
+                if isinstance(b, torch.Tensor) and b.is_cuda:
+                    return b.device
+    return None
+
+
+def on_tensor_device(fn):
+    """Decorator for the op wrappers: run `fn` with the device of its first CUDA tensor argument made current, so
+    that the launch stream, the tensor maps and the per-device function attributes all belong to the GPU that owns
+    the data (a process may drive several GPUs, and gloo-backend ranks never call set_device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

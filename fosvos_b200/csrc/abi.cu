@@ -24,13 +24,20 @@ int check_launch(const char* what) {
   return FOSVOS_OK;
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
+// SM count of the CURRENT device (a process may drive several GPUs: cached per device)
 int num_sms() {
-  static int cached = 0;
-  if (cached > 0) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  static int cached[64] = {0};
+  const int slot = device_slot();
+  if (cached[slot] > 0) return cached[slot];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot) != cudaSuccess || n <= 0) { cudaGetLastError(); return 148; }
+  cached[slot] = n;
   return n;
 }
 

@@ -25,6 +25,15 @@ static inline cudaStream_t as_stream(fosvos_stream_t s) { return reinterpret_cas
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 int num_sms();
+// Per-device one-time setup (cudaFuncSetAttribute is per device): true exactly when `done` had no bit for the CURRENT
+// device yet; sets it.  A benign race at worst repeats an idempotent attribute call.
+int device_slot();
+static inline bool first_use_on_device(unsigned long long& done) {
+  const unsigned long long bit = 1ull << device_slot();
+  if (done & bit) return false;
+  done |= bit;
+  return true;
+}
 
 // ---- element conversion -------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);

@@ -531,7 +531,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
           }
-          if (live) {
+          if (live && p.y) {                              // (y == nullptr: pool-only launch, nothing but the pooled map leaves)
             if (issuer) ptx::tma_store_wait_read<0>();    // the previous store of this group has read the buffer
             ptx::named_bar_sync(bar_a, GRP_THREADS);
             const uint32_t rowp = buf_a + row * 128;
@@ -698,11 +698,10 @@ static bool pdl_enabled() {
 template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;          // one bit per device: function attributes are per device
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
-    attr_set = true;
+    if (e != cudaSuccess) { attr_set = 0; set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
   }
   int grid = min(p.total_tiles, num_sms());
   if (const char* e = getenv("FOSVOS_TC_GRID")) { const int v = atoi(e); if (v > 0) grid = min(grid, v); }
@@ -723,7 +722,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
 
 static int conv_tc_common(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, int N,
                           int H, int W, int Cin, int Cout, int taps, int flags, fosvos_stream_t stream, const char* what) {
-  FOSVOS_REQUIRE(x && w_packed && y && N > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", what);
+  FOSVOS_REQUIRE(x && w_packed && (y || y_pool) && N > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", what);
   FOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin > 0 && Cout > 0,
                  "%s: Cin=%d and Cout=%d must be positive multiples of 8 (pad the NHWC tensors)", what, Cin, Cout);
   FOSVOS_REQUIRE(!(flags & FOSVOS_CONV_BIAS) || bias, "%s: BIAS flag without bias pointer", what);
@@ -790,7 +789,9 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
            : halo ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH + 2, TC_BK, true)
                   : encode_act_map(&mx, x, N, H, W, Cin, TW, TH, TC_BK, true);
   if (rc) return rc;
-  rc = encode_act_map(&my, y, N, H, W, Cout, TW, TH, TC_BK, true);      // output slabs leave through TMA stores (BN >= 64)
+  // output slabs leave through TMA stores (BN >= 64); a pool-only launch (y == nullptr) never issues one: its map
+  // just has to encode, so it describes the input tensor
+  rc = y ? encode_act_map(&my, y, N, H, W, Cout, TW, TH, TC_BK, true) : encode_act_map(&my, x, N, H, W, Cin, TW, TH, TC_BK, true);
   if (rc) return rc;
   rc = encode_w_map(&mw, w_packed, Cout, taps * p.cin_pad, BN);
   if (rc) return rc;

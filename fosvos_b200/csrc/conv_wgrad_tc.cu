@@ -492,11 +492,10 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   if (rc) return rc;
 
   const int smem_bytes = p.stages * p.stage_bytes + 1024 + 1024;
-  static int smem_set = 0;
-  if (smem_bytes > smem_set) {
+  static unsigned long long smem_set = 0;          // one bit per device: function attributes are per device
+  if (first_use_on_device(smem_set)) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad smem): %s", cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
-    smem_set = 226 * 1024;
+    if (e != cudaSuccess) { smem_set = 0; set_error("cudaFuncSetAttribute(wgrad smem): %s", cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
   }
   conv3x3_wgrad_tc_kernel<<<items * splits, WG_THREADS, smem_bytes, st>>>(mx, mz, p);
   return check_launch("conv3x3_wgrad_tc");

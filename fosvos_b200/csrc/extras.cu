@@ -106,7 +106,27 @@ ingest_u8_kernel(const uint8_t* __restrict__ img, T* __restrict__ y, long long p
 
 using namespace fosvos;
 
+// nn.ReLU at module granularity (introspection path: a leaf module called on its own, osvos_vgg.py:93)
+__global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = fmaxf(x[i], 0.f);
+}
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
 extern "C" {
+
+int fosvos_relu_fwd(const float* x, float* y, long long numel, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(x && y && numel > 0, "relu_fwd: bad arguments");
+  relu_fwd_kernel<<<(int)min((long long)num_sms() * 8, ceil_div_ll(numel, 256)), 256, 0, as_stream(stream)>>>(x, y, numel);
+  return check_launch("relu_fwd");
+}
+
+int fosvos_relu_bwd(const float* y, const float* dy, float* dx, long long numel, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(y && dy && dx && numel > 0, "relu_bwd: bad arguments");
+  relu_bwd_kernel<<<(int)min((long long)num_sms() * 8, ceil_div_ll(numel, 256)), 256, 0, as_stream(stream)>>>(y, dy, dx, numel);
+  return check_launch("relu_bwd");
+}
 
 int fosvos_adam_chunk_elems(void) { return ADAM_CHUNK; }
 

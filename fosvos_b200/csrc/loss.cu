@@ -210,11 +210,38 @@ mask_iou_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, lo
   }
 }
 
+// Loss bookkeeping of the fine-tune loop (train_online.py:82,98 / train_offline.py:84-88), kept on the device so that a
+// captured window needs no library kernel: total[i] = (init ? 0 : total[i]) + w * part[i];  finish: sum += total[0..n), last = total[n-1]
+__global__ void loss_accumulate_kernel(const float* __restrict__ part, const float* __restrict__ weight, float* __restrict__ total, int n, int init) {
+  const float w = weight ? *weight : 1.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) total[i] = (init ? 0.f : total[i]) + w * part[i];
+}
+__global__ void loss_window_finish_kernel(const float* __restrict__ total, int n, float* __restrict__ loss_sum, float* __restrict__ last_loss) {
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += total[i];
+    *loss_sum += s;
+    *last_loss = total[n - 1];
+  }
+}
+
 }  // namespace fosvos
 
 using namespace fosvos;
 
 extern "C" {
+
+int fosvos_loss_accumulate(const float* part, const float* weight, float* total, int n, int init, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(part && total && n > 0, "loss_accumulate: bad arguments");
+  loss_accumulate_kernel<<<1, 64, 0, as_stream(stream)>>>(part, weight, total, n, init);
+  return check_launch("loss_accumulate");
+}
+
+int fosvos_loss_window_finish(const float* total, int n, float* loss_sum, float* last_loss, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(total && loss_sum && last_loss && n > 0, "loss_window_finish: bad arguments");
+  loss_window_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(total, n, loss_sum, last_loss);
+  return check_launch("loss_window_finish");
+}
 
 size_t fosvos_bal_loss_stats_bytes(void) { return sizeof(double) * (8 + 3 * LOSS_MAX_BLOCKS); }
 

@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.nn.modules as modules
 
 from . import _lib as L
+from . import leaf
 from . import ops
 from .layers import interp_surgery
 
@@ -67,8 +68,11 @@ class OSVOS_VGG(nn.Module):
         self.fuse = nn.Conv2d(64, 1, kernel_size=1, padding=0)
         self._initialize_weights(pretrained)
 
-        self.precision = os.environ.get("FOSVOS_PRECISION", "bf16")
+        self.precision = os.environ.get("FOSVOS_PRECISION", "bf16")       # (property: also turns the leaves into fosvos_b200.leaf classes)
+        self.introspect = False                                            # True: always run module by module (hooks fire), see leaf.py
         self.fuse_pool = os.environ.get("FOSVOS_FUSE_POOL", "1") != "0"    # max pool written by the producing conv's epilogue
+        # side_prep through the row-stacked tcgen05 kernel with the 1x1 heads fused into its epilogue (conv_side_tc.cu)
+        self.side_tc = os.environ.get("FOSVOS_SIDE_TC", "1") != "0"
         # side_prep convs and weight gradients are off the critical dependency chain: issue them on a second stream so
         # their launch gaps, prologues and tail waves overlap the next layer (also inside captured CUDA graphs)
         self.overlap = os.environ.get("FOSVOS_OVERLAP", "1") != "0"
@@ -78,6 +82,15 @@ class OSVOS_VGG(nn.Module):
         self._side_params: Optional[torch.Tensor] = None
         self._side_general = False
         self._side_separable = False
+
+    @property
+    def precision(self) -> str:
+        return self.__dict__.get("_precision", "bf16")
+
+    @precision.setter
+    def precision(self, value: str) -> None:
+        self.__dict__["_precision"] = value
+        leaf.adopt(self, value)
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -149,9 +162,9 @@ class OSVOS_VGG(nn.Module):
         raise RuntimeError(f"fosvos_b200: unknown precision mode '{self.precision}'")
 
     def _wgrad_impl(self, cin_p: int) -> str:
-        # the tensor-core weight gradient needs a reasonably filled 64-channel K-slab of X; the 3-channel
-        # first layer (padded to 8) stays on the direct kernel
-        return "tc" if (self._impl() == "tc" and cin_p >= 8) else "simt"
+        # bf16 mode: every layer takes the tensor-core weight gradient, the 3-channel first layer (padded to 8) through
+        # its one-halo-box `c8` form (conv_wgrad_tc.cu)
+        return "tc" if self._impl() == "tc" else "simt"
 
     def _packed_for(self, conv: nn.Conv2d, need_dgrad: bool) -> _PackedConv:
         pc = self._packed.setdefault(id(conv), _PackedConv())
@@ -215,10 +228,8 @@ class OSVOS_VGG(nn.Module):
                                       save, want_prob, want_mask)
         if x.dim() != 4 or x.shape[1] != self.stages[0][0].in_channels:
             raise RuntimeError(f"OSVOS_VGG.forward expects (N,{self.stages[0][0].in_channels},H,W), got {tuple(x.shape)}")
-        dt = _act_dtype(self.precision)
-        impl = self._impl()
         H, W = int(x.shape[-2]), int(x.shape[-1])
-        return self._run_pipeline(ops.nchw_to_nhwc(x.float(), dt), H, W, save, want_prob, want_mask)
+        return self._run_pipeline(ops.nchw_to_nhwc(x.float(), _act_dtype(self.precision)), H, W, save, want_prob, want_mask)
 
     def _aux_stream(self, device) -> Optional[torch.cuda.Stream]:
         if not self.overlap:
@@ -228,9 +239,30 @@ class OSVOS_VGG(nn.Module):
         return self._side_stream
 
     def _run_pipeline(self, a: torch.Tensor, H: int, W: int, save: bool, want_prob: bool, want_mask: bool):
+        with torch.cuda.device(a.device):          # streams, events and launches all belong to the tensors' GPU
+            return self._run_pipeline_on_device(a, H, W, save, want_prob, want_mask)
+
+    def _run_pipeline_on_device(self, a: torch.Tensor, H: int, W: int, save: bool, want_prob: bool, want_mask: bool):
         impl = self._impl()
         main = torch.cuda.current_stream(a.device)
         aux = self._aux_stream(a.device)
+        params = self._side()
+        mode = 1 if self._side_general else (2 if self._side_separable else 0)
+        n = int(a.shape[0])
+        # side_prep through the row-stacked kernel: the two 1x1 heads of every stage leave its epilogue (fp32 accumulators),
+        # so the side-chain needs no heads launch and -- in inference -- the 16-channel maps are never written
+        stacked = impl == "tc" and self.side_tc and all(ops.side_tc_supported(ops.pad8(c.in_channels)) and c.out_channels == 16
+                                                        for c in self.side_prep)
+        fuse_heads = stacked and mode != 1
+        zs_flat = zs_views = heads = None
+        if fuse_heads:
+            hs, ws, h_, w_ = [], [], H, W
+            for _ in range(4):
+                h_, w_ = (h_ + 1) // 2, (w_ + 1) // 2
+                hs.append(h_)
+                ws.append(w_)
+            zs_flat, zs_views = ops.side_zs_workspace(n, hs, ws, a.device)
+            heads = ops.side_heads_views(params)
         conv_in: List[torch.Tensor] = []        # input activation of every stage conv, in order
         conv_out: List[torch.Tensor] = []
         pool_in: List[Optional[torch.Tensor]] = []
@@ -247,30 +279,46 @@ class OSVOS_VGG(nn.Module):
                 conv_in.append(a)
                 cp = ops.pad8(conv.out_channels)
                 if impl == "tc" and si < 4 and ci == len(convs) - 1 and cp >= 64 and a.shape[3] > 8 and self.fuse_pool:
-                    a, pooled = ops.conv3x3_pool(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU)
+                    if si == 0 and not save:
+                        # inference: nothing but the pool reads conv1_2 (stage 0 has no side output, osvos_vgg.py:63,68):
+                        # its 52 MB/frame full-resolution map is never written
+                        pooled = ops.conv3x3_pool_only(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU)
+                        a = None
+                    else:
+                        a, pooled = ops.conv3x3_pool(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU)
                 else:
                     a = ops.conv3x3(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU, impl=impl)
-                conv_out.append(a)
+                conv_out.append(a)                          # (None for a pool-only launch: inference keeps no activations)
             stage_out.append(a)
             if si > 0:
                 sp_conv = self.side_prep[si - 1]
                 pc = self._packed_for(sp_conv, need_dgrad=save)
+                want_sp = save or not fuse_heads           # the 16-channel map itself: backward and the general side path read it
+                # output allocated on the main stream (its pool), possibly written on the auxiliary one
+                sp = torch.empty((a.shape[0], a.shape[1], a.shape[2], 16), dtype=a.dtype, device=a.device) if want_sp else None
+
+                def run_side_prep(a=a, pc=pc, sp=sp, i=si - 1):
+                    if stacked:
+                        ops.conv3x3_side(a, pc.w_fwd, pc.bias, out=sp, zs=zs_views[i] if fuse_heads else None,
+                                         heads=heads[i] if fuse_heads else None, want_y=sp is not None)
+                    else:
+                        ops.conv3x3(a, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, out=sp, impl=impl)
+
                 if aux is None:
-                    sps.append(ops.conv3x3(a, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, impl=impl))
+                    run_side_prep()
                 else:
-                    # output allocated on the main stream (its pool), written on the auxiliary one
-                    sp = torch.empty((a.shape[0], a.shape[1], a.shape[2], 16), dtype=a.dtype, device=a.device)
                     ev = torch.cuda.Event()
                     ev.record(main)
                     aux.wait_event(ev)
                     with torch.cuda.stream(aux):
-                        ops.conv3x3(a, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, out=sp, impl=impl)
-                    sps.append(sp)
+                        run_side_prep()
+                sps.append(sp)
         if aux is not None:
             main.wait_stream(aux)
-        params = self._side()
-        mode = 1 if self._side_general else (2 if self._side_separable else 0)
-        outs, prob, mask = ops.side_fwd(sps, params, H, W, general=mode, want_prob=want_prob, want_mask=want_mask)
+        if fuse_heads:
+            outs, prob, mask = ops.side_fwd_heads_done(zs_flat, hs, ws, params, n, H, W, general=mode, want_prob=want_prob, want_mask=want_mask)
+        else:
+            outs, prob, mask = ops.side_fwd(sps, params, H, W, general=mode, want_prob=want_prob, want_mask=want_mask)
         saved = None
         if save:
             saved = dict(conv_in=conv_in, conv_out=conv_out, pool_in=pool_in, stage_out=stage_out, sps=sps, H=H, W=W,
@@ -279,16 +327,22 @@ class OSVOS_VGG(nn.Module):
 
     def _run_backward(self, saved, douts: Sequence[Optional[torch.Tensor]], grads: Dict[str, torch.Tensor],
                       wgrad_ws: Optional[Dict[str, torch.Tensor]] = None,
-                      taylor: Optional[Dict[str, torch.Tensor]] = None) -> None:
+                      taylor: Optional[Dict[str, torch.Tensor]] = None, stage_done=None) -> None:
         """Accumulate (+=) parameter gradients into ``grads`` (name -> fp32 tensor, reference layout).
         With ``wgrad_ws`` (conv name -> live accumulator, ``ops.wgrad_workspace``) the tensor-core weight
         gradients are left in their accumulators; the caller folds them into ``grads`` once per optimizer
         step (``ops.conv3x3_wgrad_finish``).  With ``taylor`` (stage-conv name -> (Cout,) fp32) the pruning
         criterion sum(activation * gradient) / (N H W) of every stage conv is accumulated on the way
-        (reference ``prune.py:163-178``; post-ReLU activation x masked gradient == the hooked product)."""
+        (reference ``prune.py:163-178``; post-ReLU activation x masked gradient == the hooked product).
+        ``stage_done(bucket, aux_stream)`` is called when all weight gradients of stage ``4 - bucket`` (and of the
+        ``side_prep`` conv hanging off it) have been issued -- the data-parallel trainer starts that bucket's all-reduce."""
         if self._side_general:
             raise RuntimeError("fosvos_b200: backward through non-diagonal `upscale` weights is not supported "
                                "(the reference keeps them fixed with lr=0, network_provider.py:154-155)")
+        with torch.cuda.device(saved["sps"][0].device):
+            self._run_backward_on_device(saved, douts, grads, wgrad_ws, taylor, stage_done)
+
+    def _run_backward_on_device(self, saved, douts, grads, wgrad_ws, taylor, stage_done=None) -> None:
         impl = self._impl()
         H, W = saved["H"], saved["W"]
         sps = saved["sps"]
@@ -381,6 +435,8 @@ class OSVOS_VGG(nn.Module):
                 pc = self._packed_for(conv, need_dgrad=True)
                 # dX masked by (x_in > 0): x_in is the previous layer's post-ReLU output (or its pooled copy)
                 dz = ops.conv3x3(dz, pc.w_dgrad, None, x_in.shape[3], L.CONV_MASK, mask=x_in, impl=impl)
+            if stage_done is not None:
+                stage_done(4 - si, aux)
             if si > 0:
                 if si - 1 > 0 and side_done[si - 1] is not None:
                     main.wait_event(side_done[si - 1])
@@ -392,7 +448,36 @@ class OSVOS_VGG(nn.Module):
     def _grad_names(self) -> List[str]:
         return [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("upscale")]
 
+    # ------------------------------------------------------------------ introspection (module by module)
+    def _leaf_hooks_present(self) -> bool:
+        for root in (self.stages, self.side_prep):
+            for m in root.modules():
+                if m._forward_hooks or m._forward_pre_hooks:
+                    return True
+        return False
+
+    def _forward_introspect(self, x: torch.Tensor):
+        """Module-by-module forward for hook-style consumers (prune.py:94-103; SURVEY 8b "hookable per-conv outputs"): every
+        leaf of ``stages`` / ``side_prep`` is CALLED (so ``register_forward_hook`` fires, and tensor hooks registered on the
+        outputs fire in backward), each running this repo's kernels through ``leaf.py``; the side chain stays one fused
+        node.  Slower than the fused pipeline (layout changes around every module); same arithmetic."""
+        L.require_device(x.device)
+        if x.dtype == torch.uint8 or x.dim() != 4:
+            raise RuntimeError("OSVOS_VGG introspection mode expects the reference contract: (N,C,H,W) float frames")
+        leaf.adopt(self, self.precision)             # surgery may have assigned plain torch leaves
+        H, W = int(x.shape[-2]), int(x.shape[-1])
+        a = x.float()
+        sps = []
+        for si, stage in enumerate(self.stages):
+            a = stage(a)                              # osvos_vgg.py:63,68
+            if si > 0:
+                sps.append(self.side_prep[si - 1](a))   # :69
+        heads = [m.weight for m in self.score_dsn] + [m.bias for m in self.score_dsn]
+        return list(_SideChainFunction.apply(self, H, W, self.fuse.weight, self.fuse.bias, *heads, *sps))
+
     def forward(self, x):
+        if self.introspect or self._leaf_hooks_present():
+            return self._forward_introspect(x)
         params = dict(self.named_parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params.values()):
             names = self._grad_names()
@@ -420,11 +505,50 @@ class _OSVOSFunction(torch.autograd.Function):
         ctx.net, ctx.saved, ctx.names = net, saved, names
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.device = x.device
+        # outputs without a consumer hand backward None instead of a zero-filled full-resolution map: the online loop
+        # uses outputs[-1] only (train_online.py:81), so the four side-map gradients are skipped, not multiplied by zero
+        ctx.set_materialize_grads(False)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
+        if ctx.saved is None:
+            raise RuntimeError("OSVOS_VGG: the activations of this forward pass were released by the first backward "
+                               "(call forward again; retain_graph=True is not supported by the fused backward)")
         grads = {n: torch.zeros(s, dtype=torch.float32, device=ctx.device) for n, s in zip(ctx.names, ctx.shapes)}
         ctx.net._run_backward(ctx.saved, [None if d is None else d.contiguous() for d in douts], grads)
         ctx.saved = None
         return (None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+class _SideChainFunction(torch.autograd.Function):
+    """The fused side chain (osvos_vgg.py:71-81) as one autograd node of the introspection path: four side_prep maps
+    (N,16,h,w) -> [side0..3, fused]."""
+
+    @staticmethod
+    def forward(ctx, net: OSVOS_VGG, H, W, fuse_w, fuse_b, sw0, sw1, sw2, sw3, sb0, sb1, sb2, sb3, *sps):
+        dt = _act_dtype(net.precision)
+        params = net._side()
+        mode = 1 if net._side_general else (2 if net._side_separable else 0)
+        sph = [ops.nchw_to_nhwc(t.detach().float().contiguous(), dt, cp=16) for t in sps]
+        outs, _, _ = ops.side_fwd(sph, params, H, W, general=mode)
+        ctx.net, ctx.sph, ctx.params, ctx.hw = net, sph, params, (H, W)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        net = ctx.net
+        if net._side_general:
+            raise RuntimeError("fosvos_b200: backward through non-diagonal `upscale` weights is not supported "
+                               "(the reference keeps them fixed with lr=0, network_provider.py:154-155)")
+        H, W = ctx.hw
+        dev = ctx.sph[0].device
+        douts = [None if d is None else d.float().contiguous() for d in douts]
+        if douts[4] is None:
+            douts[4] = torch.zeros((ctx.sph[0].shape[0], 1, H, W), dtype=torch.float32, device=dev)
+        dfw, dfb = torch.zeros_like(net.fuse.weight), torch.zeros_like(net.fuse.bias)
+        dsw = [torch.zeros_like(m.weight) for m in net.score_dsn]
+        dsb = [torch.zeros_like(m.bias) for m in net.score_dsn]
+        dsp = ops.side_bwd(ctx.sph, ctx.params, douts, H, W, dfw, dfb, dsw, dsb)
+        dsp_nchw = [ops.nhwc_to_nchw(t, 16) for t in dsp]
+        return (None, None, None, dfw, dfb, *dsw, *dsb, *dsp_nchw)

@@ -14,7 +14,8 @@ frame size and reused for every sequence the process handles.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+import functools
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -22,7 +23,19 @@ from . import _lib as L
 from . import ops
 from .networks import OSVOS_VGG, _act_dtype
 from .optim import FusedSGD, get_optimizer_online
-from .sharding import allreduce_flat
+from .sharding import GradBuckets, allreduce_flat
+
+
+def _on_device(fn):
+    """Run a trainer method with the trainer's GPU current (streams, graphs and launches belong to it)."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+MAX_RESIDENT_TRAINERS = 6        # 3 train-time scales x {plain, flipped} share a size: 6 covers every shape of SURVEY section 7 step 5
 
 
 def _repack_in_place(net: OSVOS_VGG) -> None:
@@ -101,7 +114,15 @@ class OnlineTrainer:
 
     def __init__(self, net: OSVOS_VGG, height: int, width: int, avg_grad_every_n: int = 5,
                  optimizer: Optional[FusedSGD] = None, use_graph: bool = True, deep_supervision: Optional[float] = None,
-                 data_parallel: bool = False, world_size: int = 1, fuse_window: bool = True):
+                 data_parallel: bool = False, world_size: int = 1, fuse_window: bool = True,
+                 share_with: Optional["OnlineTrainer"] = None, overlap_allreduce: bool = True):
+        self.device = next(net.parameters()).device
+        with torch.cuda.device(self.device):
+            self._init(net, height, width, avg_grad_every_n, optimizer, use_graph, deep_supervision, data_parallel, world_size,
+                       fuse_window, share_with, overlap_allreduce)
+
+    def _init(self, net, height, width, avg_grad_every_n, optimizer, use_graph, deep_supervision, data_parallel, world_size,
+              fuse_window, share_with, overlap_allreduce):
         """``fuse_window``: the ``avg_grad_every_n`` micro-iterations between two optimizer steps all see the SAME weights
         and their gradients are summed, so they are independent of each other: run them as ONE batched
         forward/backward over the window's frames (every frame is still computed in full, each with its own loss and
@@ -110,8 +131,14 @@ class OnlineTrainer:
         ``data_parallel``: offline parent training sharded over ``world_size`` ranks (one process per GPU): every
         rank runs ``avg_grad_every_n // world_size`` micro-iterations on its own frames, gradients (scaled by
         1/avg_grad_every_n as in the reference) are summed with ONE all-reduce of a flat fp32 buffer, then every
-        rank applies the same optimizer step."""
-        dev = next(net.parameters()).device
+        rank applies the same optimizer step.  With ``overlap_allreduce`` the flat buffer is laid out in per-stage buckets
+        (deepest stage first, the order the backward pass finishes them) and every bucket's weight-gradient fold +
+        all-reduce is issued on a side stream as soon as that stage's weight gradients are done, so the exchange hides
+        behind the rest of the backward pass (needs the fused window, runs it outside CUDA graphs).
+        ``share_with``: another trainer of the same network (a different frame size): gradients, weight-gradient
+        accumulators, optimizer (momentum), counters and the optimizer-step graph are SHARED, so consecutive iterations may
+        alternate between frame sizes (train-time Resize scales, custom_transforms.py:63-109) without re-capturing."""
+        dev = self.device
         L.require_device(dev)
         self.net = net
         self.data_parallel = bool(data_parallel) and world_size > 1
@@ -122,8 +149,13 @@ class OnlineTrainer:
         self.deep = deep_supervision
         # the side-loss weight (1 - epoch / n_epochs, train_offline.py:88) lives on the device: captured graphs read it
         self.deep_w = None if deep_supervision is None else torch.full((), float(deep_supervision), dtype=torch.float32, device=dev)
-        self.optimizer = optimizer if optimizer is not None else get_optimizer_online(net)
+        sh = share_with._shared if share_with is not None else None
+        if sh is not None and optimizer is not None and optimizer is not sh["optimizer"]:
+            raise ValueError("share_with: the shared trainer already owns the optimizer")
+        self.optimizer = sh["optimizer"] if sh is not None else (optimizer if optimizer is not None else get_optimizer_online(net))
         self.fused = isinstance(self.optimizer, FusedSGD)
+        self.overlap_ar = self.data_parallel and bool(overlap_allreduce) and self.fused and net._impl() == "tc" and \
+            bool(fuse_window) and self.n > 1 and sh is None
         self.use_graph = bool(use_graph) and self.fused
         self.fuse = bool(fuse_window) and self.n > 1
         slots = self.n if self.fuse else 1
@@ -132,45 +164,86 @@ class OnlineTrainer:
         self.masks = torch.zeros((slots, 1, height, width), dtype=torch.float32, device=dev)
         self.frame, self.mask = self.frames[0:1], self.masks[0:1]
         self.window_losses = torch.zeros(slots, dtype=torch.float32, device=dev)
+        self._part_losses = torch.zeros(slots, dtype=torch.float32, device=dev)
         params = dict(net.named_parameters())
-        self.grads: Dict[str, torch.Tensor] = {}
-        self.flat_grad = None
-        if self.data_parallel:
-            names = net._grad_names()
-            self.flat_grad = torch.zeros(sum(params[n].numel() for n in names), dtype=torch.float32, device=dev)
-            off = 0
-            for name in names:
+        if sh is not None:
+            self._shared = sh
+        else:
+            grads: Dict[str, torch.Tensor] = {}
+            flat_grad, buckets = None, None
+            if self.data_parallel:
+                # one flat fp32 buffer, bucket-major: [stage 4 + side_prep.3][stage 3 + side_prep.2] ... [stage 0][heads]
+                buckets = GradBuckets(net, params, dev)
+                flat_grad = buckets.flat
+            for name in net._grad_names():
                 p = params[name]
-                p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
-                off += p.numel()
-        for name in net._grad_names():
-            p = params[name]
-            if p.grad is None:
-                p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            self.grads[name] = p.grad
-        # tensor-core weight gradients accumulate in their own [tap][M][N] layout over the micro-iterations and are
-        # folded into .grad once per optimizer step
-        self.wgrad_ws: Optional[Dict[str, torch.Tensor]] = None
-        if self.fused and net._impl() == "tc":
-            self.wgrad_ws = {}
-            for name in self.grads:
-                if name.endswith(".weight") and params[name].dim() == 4 and tuple(params[name].shape[2:]) == (3, 3):
-                    cout, cin = params[name].shape[0], params[name].shape[1]
-                    self.wgrad_ws[name[:-len(".weight")]] = ops.wgrad_workspace(ops.pad8(cin), ops.pad8(cout), dev)
-        self._fold_table = None
+                if buckets is not None:
+                    p.grad = buckets.view(name)
+                elif p.grad is None:
+                    p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                grads[name] = p.grad
+            # tensor-core weight gradients accumulate in their own [tap][M][N] layout over the micro-iterations and are
+            # folded into .grad once per optimizer step
+            wgrad_ws: Optional[Dict[str, torch.Tensor]] = None
+            if self.fused and net._impl() == "tc":
+                wgrad_ws = {}
+                for name in grads:
+                    if name.endswith(".weight") and params[name].dim() == 4 and tuple(params[name].shape[2:]) == (3, 3):
+                        cout, cin = params[name].shape[0], params[name].shape[1]
+                        wgrad_ws[name[:-len(".weight")]] = ops.wgrad_workspace(ops.pad8(cin), ops.pad8(cout), dev)
+            self._shared = dict(optimizer=self.optimizer, grads=grads, flat_grad=flat_grad, buckets=buckets, wgrad_ws=wgrad_ws,
+                                fold_table=None, step_graph=None, calls_step=0, step_gen=-1, counter=0,
+                                loss_sum=torch.zeros((), dtype=torch.float32, device=dev),
+                                last_loss=torch.zeros((), dtype=torch.float32, device=dev))
+        self.grads = self._shared["grads"]
+        self.flat_grad = self._shared["flat_grad"]
+        self.wgrad_ws = self._shared["wgrad_ws"]
         # label counts of the resident mask: they only change with set_frame(), so loss and gradient are ONE pass
         self.loss_stats_all = torch.zeros((slots, L.lib().fosvos_bal_loss_stats_bytes() // 8), dtype=torch.float64, device=dev)
         self.loss_stats = self.loss_stats_all[0]
         self._label_counts()
-        self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
-        self.last_loss = torch.zeros((), dtype=torch.float32, device=dev)
-        self.counter = 0
+        self.loss_sum = self._shared["loss_sum"]
+        self.last_loss = self._shared["last_loss"]
+        self._micro_total = torch.zeros(1, dtype=torch.float32, device=dev)
         self._micro_graph = None
         self._window_graph = None
-        self._step_graph = None
         self._calls_micro = 0
         self._calls_window = 0
-        self._calls_step = 0
+        self._comm_stream: Optional[torch.cuda.Stream] = None
+        self.exposed_allreduce_ms: Optional[float] = None
+
+    # shared between the trainers of one network (see ``share_with``)
+    @property
+    def counter(self) -> int:
+        return self._shared["counter"]
+
+    @counter.setter
+    def counter(self, v: int) -> None:
+        self._shared["counter"] = v
+
+    @property
+    def _fold_table(self):
+        return self._shared["fold_table"]
+
+    @_fold_table.setter
+    def _fold_table(self, v) -> None:
+        self._shared["fold_table"] = v
+
+    @property
+    def _step_graph(self):
+        return self._shared["step_graph"]
+
+    @_step_graph.setter
+    def _step_graph(self, v) -> None:
+        self._shared["step_graph"] = v
+
+    @property
+    def _calls_step(self) -> int:
+        return self._shared["calls_step"]
+
+    @_calls_step.setter
+    def _calls_step(self, v: int) -> None:
+        self._shared["calls_step"] = v
 
     # ---------------------------------------------------------------- pieces
     def _label_counts(self) -> None:
@@ -189,25 +262,48 @@ class OnlineTrainer:
                                                   losses=self.window_losses)
         if self.deep_w is not None:
             for j in range(4):
-                lj, douts[j] = ops.bal_loss_fwd_bwd_frames(outs[j], self.masks, False, self.loss_stats_all, self.deep_w, self.scale)
-                self.window_losses.add_(self.deep_w * lj)
-        self.last_loss.copy_(self.window_losses[n - 1])
-        self.loss_sum.add_(self.window_losses.sum())
-        net._run_backward(saved, douts, self.grads, self.wgrad_ws)
+                _, douts[j] = ops.bal_loss_fwd_bwd_frames(outs[j], self.masks, False, self.loss_stats_all, self.deep_w, self.scale,
+                                                          losses=self._part_losses)
+                ops.loss_accumulate(self._part_losses, self.window_losses, self.deep_w)
+        ops.loss_window_finish(self.window_losses, self.loss_sum, self.last_loss)
+        net._run_backward(saved, douts, self.grads, self.wgrad_ws, **self._backward_hooks())
 
     def _micro(self) -> None:
         net = self.net
         outs, _, _, saved = net._run_forward(self.frame, save=True)
         douts: List[Optional[torch.Tensor]] = [None] * 5
         loss, douts[4] = ops.bal_loss_fwd_bwd(outs[4], self.mask, False, self.loss_stats, None, self.scale)
-        total = loss
+        ops.loss_accumulate(loss.view(1), self._micro_total, None, init=True)
         if self.deep_w is not None:
             for i in range(4):
                 li, douts[i] = ops.bal_loss_fwd_bwd(outs[i], self.mask, False, self.loss_stats, self.deep_w, self.scale)
-                total = total + self.deep_w * li
-        self.last_loss.copy_(total)
-        self.loss_sum.add_(total)
+                ops.loss_accumulate(li.view(1), self._micro_total, self.deep_w)
+        ops.loss_window_finish(self._micro_total, self.loss_sum, self.last_loss)
         net._run_backward(saved, douts, self.grads, self.wgrad_ws)
+
+    def _backward_hooks(self) -> dict:
+        """Data-parallel overlap: a callback the backward pass fires when a stage's weight gradients have been issued
+        (``OSVOS_VGG._run_backward(stage_done=...)``): fold that bucket's accumulators and all-reduce it on the side stream."""
+        if not self.overlap_ar:
+            return {}
+        return {"stage_done": self._bucket_ready}
+
+    def _bucket_ready(self, bucket: int, aux_stream: Optional[torch.cuda.Stream]) -> None:
+        bk = self._shared["buckets"]
+        comm = self._comm_stream
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(aux_stream if aux_stream is not None else main)        # the bucket's weight gradients run there
+        comm.wait_event(ev)
+        if bucket == bk.n_buckets - 1:
+            ev2 = torch.cuda.Event()
+            ev2.record(main)                                             # the heads' gradients (side_bwd) run on the main stream
+            comm.wait_event(ev2)
+        with torch.cuda.stream(comm):
+            tab = bk.fold_table(bucket, self.wgrad_ws, self.grads)
+            if tab is not None:
+                ops.wgrad_fold_all(tab)
+            self._ar_works.append(bk.allreduce(bucket))
 
     def _fold_wgrads(self) -> None:
         if self.wgrad_ws:
@@ -216,6 +312,7 @@ class OnlineTrainer:
                                                   self.frame.device)
             ops.wgrad_fold_all(self._fold_table)
 
+    @_on_device
     def set_deep_supervision(self, weight: float) -> None:
         """New epoch: side-loss weight ``1 - epoch / n_epochs`` (train_offline.py:88); no re-capture needed."""
         self.deep_w.fill_(float(weight))
@@ -237,6 +334,14 @@ class OnlineTrainer:
         import os
         assert self.counter == 0, "graphs are captured at a window boundary (the warm-up pass clears the gradient accumulators)"
         body = self._window if window else self._micro
+        hooks, self.overlap_ar = self.overlap_ar, False        # (the overlapped data-parallel window is never captured)
+        try:
+            self._capture_body(body, window)
+        finally:
+            self.overlap_ar = hooks
+
+    def _capture_body(self, body, window: bool) -> None:
+        import os
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -256,7 +361,7 @@ class OnlineTrainer:
             _repack_in_place(self.net)              # builds the multi-tensor repack table (host -> device copies)
         torch.cuda.current_stream().wait_stream(s)
         graph = torch.cuda.CUDAGraph()
-        pool = next((g.pool() for g in (self._micro_graph, self._window_graph, self._step_graph) if g is not None), None)
+        pool = next((g.pool() for g in (self._micro_graph, self._window_graph, self._step_graph) if g is not None), None)   # one pool per network
         # captured on a high-priority stream: the dependency chain (forward, data gradients) wins the SMs over the
         # weight gradients / side branches that the network issues on its default-priority auxiliary stream
         hp = torch.cuda.Stream(priority=-1 if os.environ.get("FOSVOS_HP", "1") != "0" else 0)
@@ -269,15 +374,34 @@ class OnlineTrainer:
         else:
             self._micro_graph, self._calls_micro = graph, calls
         if self._step_graph is None:
-            c0 = L.CALLS[0]
-            self._step_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._step_graph, pool=graph.pool()):
-                self._step()
-            self._calls_step = L.CALLS[0] - c0
+            self._capture_step(graph.pool())
         # capture does not execute: gradients are still zero, parameters untouched; versions were bumped
         _sync_cache_keys(self.net)
 
+    def _capture_step(self, pool=None) -> None:
+        self.optimizer._ensure_table()
+        c0 = L.CALLS[0]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, **({} if pool is None else {"pool": pool})):
+            self._step()
+        self._step_graph = g
+        self._calls_step = L.CALLS[0] - c0
+        self._shared["step_gen"] = self.optimizer._table_gen
+        _sync_cache_keys(self.net)
+
     # ---------------------------------------------------------------- public
+    @_on_device
+    def prepare(self, window: Optional[bool] = None) -> None:
+        """Capture this trainer's CUDA graphs now (at a window boundary) instead of on first use."""
+        if not self.use_graph:
+            return
+        window = self.fuse if window is None else window
+        if window and self._window_graph is None and not self.overlap_ar:
+            self._capture(window=True)
+        if not window and self._micro_graph is None:
+            self._capture(window=False)
+
+    @_on_device
     def reset(self, state_dict: Optional[dict] = None) -> None:
         """Start a new sequence: (optionally) reload the parent weights in place
         (``NetworkProvider.load_model``, network_provider.py:53-58), clear gradients and momentum."""
@@ -299,6 +423,7 @@ class OnlineTrainer:
             self.net._side_key = None          # new up-sampling weights: re-run the structure check (one sync,
             self.net._side()                   # outside any graph) and rebuild the parameter block in place
 
+    @_on_device
     def set_frame(self, frame: torch.Tensor, mask: torch.Tensor) -> None:
         """Copy the annotated frame (1,3,H,W) and its mask (1,1,H,W) into the resident buffers -- into every slot of
         the window: each micro-iteration reads its own copy (host tensors are uploaded; pinned ones asynchronously)."""
@@ -309,17 +434,24 @@ class OnlineTrainer:
             self.masks[i:i + 1].copy_(self.mask)
         self._label_counts()                                                      # label counts of the new mask(s)
 
+    @_on_device
     def set_frames(self, frames: torch.Tensor, masks: torch.Tensor) -> None:
         """Distinct frames for the micro-iterations of a window (e.g. flipped copies): (n,3,H,W) and (n,1,H,W)."""
         self.frames.copy_(frames.reshape(self.frames.shape), non_blocking=True)
         self.masks.copy_(masks.reshape(self.masks.shape), non_blocking=True)
         self._label_counts()
 
-    def _optimizer_step(self) -> None:
-        self._fold_wgrads()
-        if self.data_parallel:
-            allreduce_flat(self.flat_grad)
+    def _optimizer_step(self, exchanged: bool = False) -> None:
+        if not exchanged:
+            self._fold_wgrads()
+            if self.data_parallel:
+                allreduce_flat(self.flat_grad)
         if self.use_graph:
+            # param_groups (lr, weight decay) or momentum buffers changed since the capture?  The device table is rewritten
+            # in place; only a new geometry / momentum needs a fresh capture of the step
+            self.optimizer._ensure_table()
+            if self._step_graph is None or self._shared["step_gen"] != self.optimizer._table_gen:
+                self._capture_step(next((g.pool() for g in (self._micro_graph, self._window_graph) if g is not None), None))
             self._step_graph.replay()
             L.CALLS[0] += self._calls_step
             for p in self.net.parameters():
@@ -328,6 +460,21 @@ class OnlineTrainer:
         else:
             self._step()
 
+    def _window_overlapped(self) -> None:
+        """Data-parallel window with the exchange overlapped: eager launches (the NCCL calls sit between them), per-stage
+        buckets folded and all-reduced on a side stream while the backward pass continues."""
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        self._ar_works = []
+        self._window()
+        main = torch.cuda.current_stream(self.device)
+        for w in self._ar_works:
+            if w is not None:
+                w.wait()                                # the main stream waits for the reduced bucket
+        main.wait_stream(self._comm_stream)
+        self._ar_works = []
+
+    @_on_device
     def run(self, n_iters: int, losses_out: Optional[list] = None) -> torch.Tensor:
         if self.use_graph and (self._micro_graph is not None or self._window_graph is not None) and not _keys_current(self.net):
             _repack_in_place(self.net)          # parameters were changed from outside since the last replay
@@ -335,6 +482,15 @@ class OnlineTrainer:
         while done < n_iters:
             if self.fuse and self.counter == 0 and n_iters - done >= self.n:
                 # a whole accumulation window: one batched pass
+                if self.overlap_ar:
+                    if self.use_graph and self._step_graph is None:
+                        self._capture_overlap_warmup()
+                    self._window_overlapped()
+                    if losses_out is not None:
+                        losses_out.extend(float(v) for v in self.window_losses.tolist())
+                    done += self.n
+                    self._optimizer_step(exchanged=True)
+                    continue
                 if self.use_graph:
                     if self._window_graph is None:
                         self._capture(window=True)
@@ -364,6 +520,30 @@ class OnlineTrainer:
         return self.loss_sum
 
 
+def _capture_overlap_warmup(self: OnlineTrainer) -> None:
+    """First overlapped window of a data-parallel trainer: warm up once (packs weights, builds the tables), clear what the
+    warm-up accumulated, capture the optimizer-step graph."""
+    saved_sum = self.loss_sum.clone()
+    self._ar_works = []
+    hooks, self.overlap_ar = self.overlap_ar, False
+    try:
+        self._window()
+    finally:
+        self.overlap_ar = hooks
+    torch.cuda.current_stream(self.device).synchronize()
+    for g in self.grads.values():
+        g.zero_()
+    for ws in (self.wgrad_ws or {}).values():
+        ws.zero_()
+    self.loss_sum.copy_(saved_sum)
+    self.optimizer._ensure_table()
+    _repack_in_place(self.net)
+    self._capture_step(None)
+
+
+OnlineTrainer._capture_overlap_warmup = _capture_overlap_warmup
+
+
 def finetune(net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, n_iters: int, avg_grad_every_n: int = 5,
              optimizer: Optional[FusedSGD] = None, use_graph: bool = False,
              losses_out: Optional[list] = None) -> torch.Tensor:
@@ -377,7 +557,10 @@ def finetune(net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, n_iters: i
     cache = net.__dict__.setdefault("_trainers", {})
     tr = cache.get(key)
     if tr is None:
-        cache.clear()                           # one resident trainer per net: graphs pin a lot of memory
+        # trainers (and their captured graphs) stay resident per frame size -- the online loop alternates between the
+        # three train-time scales of 480x854 (custom_transforms.py:63-109); the oldest is dropped beyond MAX_RESIDENT_TRAINERS
+        while len(cache) >= MAX_RESIDENT_TRAINERS:
+            cache.pop(next(iter(cache)))
         tr = OnlineTrainer(net, key[0], key[1], avg_grad_every_n, optimizer, use_graph)
         cache[key] = tr
     elif optimizer is None:
@@ -387,6 +570,49 @@ def finetune(net: OSVOS_VGG, frame: torch.Tensor, mask: torch.Tensor, n_iters: i
         tr.counter = 0
     tr.set_frame(frame, mask)
     return tr.run(n_iters, losses_out)
+
+
+def finetune_samples(net: OSVOS_VGG, samples: Sequence[Tuple[torch.Tensor, torch.Tensor]], avg_grad_every_n: int = 5,
+                     optimizer: Optional[FusedSGD] = None, use_graph: bool = True, losses_out: Optional[list] = None) -> torch.Tensor:
+    """The online loop over an explicit list of per-iteration samples ``[(frame (1,3,h,w), mask (1,1,h,w)), ...]`` whose
+    sizes may differ from one iteration to the next -- what the reference's loader delivers with train-time augmentation
+    on (random flip, Resize scale in {0.5, 0.8, 1}: ``io_helper.py:62-70``, ``custom_transforms.py:63-109``; 480x854 gives
+    240x427, 384x683, 480x854).  One resident trainer (and CUDA graph of the micro-iteration) per frame size; gradients,
+    momentum, the accumulation counter and the optimizer-step graph are shared between them, so alternating sizes costs
+    a graph replay, never a re-capture.  Returns the device scalar of the summed per-iteration losses."""
+    dev = next(net.parameters()).device
+    L.require_device(dev)
+    n = int(avg_grad_every_n)
+    key0 = (n, bool(use_graph), id(optimizer), net.precision)
+    cache = net.__dict__.setdefault("_sample_trainers", {})
+    if cache.get("key") != key0:
+        cache.clear()
+        cache["key"], cache["base"], cache["by_size"] = key0, None, {}
+    by_size = cache["by_size"]
+    if cache["base"] is not None:
+        base = cache["base"]
+        if optimizer is None:
+            base.reset()                                # a fresh optimizer state per call, like get_optimizer() per sequence
+        else:
+            base.loss_sum.zero_()
+            base.counter = 0
+    for frame, _ in samples:                           # every size is captured at a window boundary, before the loop
+        hw = (int(frame.shape[-2]), int(frame.shape[-1]))
+        if hw not in by_size:
+            if len(by_size) >= MAX_RESIDENT_TRAINERS:
+                raise RuntimeError(f"finetune_samples: more than {MAX_RESIDENT_TRAINERS} distinct frame sizes")
+            tr = OnlineTrainer(net, hw[0], hw[1], n, optimizer if cache["base"] is None else None, use_graph, fuse_window=False,
+                               share_with=cache["base"])
+            if cache["base"] is None:
+                cache["base"] = tr
+            tr.prepare()
+            by_size[hw] = tr
+    base = cache["base"]
+    for frame, mask in samples:
+        tr = by_size[(int(frame.shape[-2]), int(frame.shape[-1]))]
+        tr.set_frame(frame, mask)
+        tr.run(1, losses_out)
+    return base.loss_sum
 
 
 @torch.no_grad()

@@ -98,6 +98,43 @@ def conv3x3_pool(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
     return y, yp
 
 
+def conv3x3_pool_only(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout_p: int, flags: int) -> torch.Tensor:
+    """Same launch with the full-resolution output suppressed: only the pooled map leaves the kernel (inference, when
+    nothing but the pool consumes the conv -- conv1_2, osvos_vgg.py:63,68)."""
+    L.require_device(x.device)
+    n, h, w, cin_p = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    yp = torch.empty((n, (h + 1) // 2, (w + 1) // 2, cout_p), dtype=x.dtype, device=x.device)
+    L.check(L.lib().fosvos_conv3x3_tc_pool(x.data_ptr(), w_packed.data_ptr(), L.ptr(bias), None, yp.data_ptr(),
+                                           n, h, w, cin_p, cout_p, flags, L.stream()), "conv3x3_tc_pool")
+    return yp
+
+
+def side_tc_supported(cin_p: int) -> bool:
+    return bool(L.lib().fosvos_conv3x3_side_tc_supported(int(cin_p)))
+
+
+def conv3x3_side(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                 zs: Optional[torch.Tensor] = None, heads: Optional[torch.Tensor] = None, want_y: bool = True) -> Optional[torch.Tensor]:
+    """side_prep convolution (C -> 16, bias, no ReLU; osvos_vgg.py:42,69) through the row-stacked tcgen05 kernel.
+    ``zs`` (N*h*w, 2) fp32: the two 1x1 heads of the side chain are written there from the fp32 accumulators, with
+    ``heads`` the stage's 36 head parameters (a view into the side-chain parameter block).  Returns y (N,h,w,16) bf16
+    (or None with ``want_y=False``)."""
+    L.require_device(x.device)
+    n, h, w, cin_p = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    if want_y and out is None:
+        out = torch.empty((n, h, w, 16), dtype=x.dtype, device=x.device)
+    if out is not None:
+        assert out.shape == (n, h, w, 16) and out.dtype == x.dtype and out.is_contiguous()
+    if zs is not None:
+        assert zs.dtype == torch.float32 and zs.numel() == 2 * n * h * w and zs.is_contiguous()
+        assert heads is not None and heads.dtype == torch.float32 and heads.numel() >= 36
+    L.check(L.lib().fosvos_conv3x3_side_tc(x.data_ptr(), w_packed.data_ptr(), L.ptr(bias), L.ptr(out), L.ptr(zs), L.ptr(heads),
+                                           n, h, w, cin_p, L.stream()), "conv3x3_side_tc")
+    return out
+
+
 def wgrad_workspace(cin_p: int, cout_p: int, device) -> torch.Tensor:
     """Zeroed [tap][M][N] fp32 accumulator of the tensor-core weight gradient (kept live across micro-iterations)."""
     return torch.zeros(L.lib().fosvos_conv3x3_wgrad_tc_workspace_bytes(cin_p, cout_p) // 4, dtype=torch.float32, device=device)
@@ -218,6 +255,36 @@ def side_fwd(sp: Sequence[torch.Tensor], params: torch.Tensor, H: int, W: int, g
     return outs, prob, mask
 
 
+def side_heads_views(params: torch.Tensor) -> List[torch.Tensor]:
+    """Per stage the 36 head parameters {score_dsn.w[16], score_dsn.b, 3 unused, fuse.w[16 i ..]} inside a prepared block."""
+    return [params[L.lib().fosvos_side_params_heads_offset(i):L.lib().fosvos_side_params_heads_offset(i) + 36] for i in range(4)]
+
+
+def side_zs_workspace(n: int, hs: Sequence[int], ws: Sequence[int], device) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """The low-res head maps of a batch, stage after stage ((N,h_i,w_i) float2 each), and the per-stage views."""
+    sizes = [n * h * w for h, w in zip(hs, ws)]
+    flat = torch.empty((sum(sizes), 2), dtype=torch.float32, device=device)
+    views, off = [], 0
+    for sz in sizes:
+        views.append(flat[off:off + sz])
+        off += sz
+    return flat, views
+
+
+def side_fwd_heads_done(zs: torch.Tensor, hs: Sequence[int], ws: Sequence[int], params: torch.Tensor, n: int, H: int, W: int,
+                        general: int = 2, want_prob: bool = False, want_mask: bool = False):
+    """``side_fwd`` fast paths (general 0 / 2) from head maps the side_prep convolutions already wrote (``conv3x3_side``)."""
+    dev = params.device
+    L.require_device(dev)
+    assert int(general) in (0, 2) and zs.dtype == torch.float32 and zs.numel() == 2 * sum(n * h * w for h, w in zip(hs, ws))
+    outs = [torch.empty((n, 1, H, W), dtype=torch.float32, device=dev) for _ in range(5)]
+    prob = torch.empty((n, 1, H, W), dtype=torch.float32, device=dev) if want_prob else None
+    mask = torch.empty((n, 1, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+    L.check(L.lib().fosvos_side_fwd_heads_done(L.int_array(list(hs)), L.int_array(list(ws)), params.data_ptr(), L.ptr_array(outs),
+                                               L.ptr(prob), L.ptr(mask), zs.data_ptr(), int(general), n, H, W, L.stream()), "side_fwd_heads_done")
+    return outs, prob, mask
+
+
 def side_bwd(sp: Sequence[torch.Tensor], params: torch.Tensor, dout: Sequence[Optional[torch.Tensor]], H: int, W: int,
              d_fuse_w: Optional[torch.Tensor], d_fuse_b: Optional[torch.Tensor],
              d_score_w: Optional[Sequence[Optional[torch.Tensor]]], d_score_b: Optional[Sequence[Optional[torch.Tensor]]]) -> List[torch.Tensor]:
@@ -299,6 +366,20 @@ def bal_loss_bwd(output: torch.Tensor, label: torch.Tensor, size_average: bool, 
                                         stats.data_ptr(), L.ptr(grad_out), float(grad_scale), dx.data_ptr(), L.stream()),
             "bal_loss_bwd")
     return dx
+
+
+def loss_accumulate(part: torch.Tensor, total: torch.Tensor, weight: Optional[torch.Tensor] = None, init: bool = False) -> None:
+    """total[i] = (0 if init else total[i]) + weight * part[i]  (weight: 0-dim device tensor or None = 1)."""
+    L.require_device(total.device)
+    assert part.dtype == total.dtype == torch.float32 and part.numel() == total.numel()
+    L.check(L.lib().fosvos_loss_accumulate(part.data_ptr(), L.ptr(weight), total.data_ptr(), total.numel(), int(init), L.stream()), "loss_accumulate")
+
+
+def loss_window_finish(total: torch.Tensor, loss_sum: torch.Tensor, last_loss: torch.Tensor) -> None:
+    """loss_sum += sum(total); last_loss = total[-1]."""
+    L.require_device(total.device)
+    L.check(L.lib().fosvos_loss_window_finish(total.data_ptr(), total.numel(), loss_sum.data_ptr(), last_loss.data_ptr(), L.stream()),
+            "loss_window_finish")
 
 
 # ---- optimizer-step companions (one launch for all layers) -------------------------------------
@@ -420,6 +501,24 @@ def pixel_loss(output: torch.Tensor, target: torch.Tensor, kind: str, size_avera
     return loss, dx
 
 
+def relu_fwd(x: torch.Tensor) -> torch.Tensor:
+    L.require_device(x.device)
+    assert x.dtype == torch.float32
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    L.check(L.lib().fosvos_relu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), L.stream()), "relu_fwd")
+    return y
+
+
+def relu_bwd(y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    L.require_device(y.device)
+    assert y.dtype == torch.float32 and dy.dtype == torch.float32 and y.numel() == dy.numel()
+    y, dy = y.contiguous(), dy.contiguous()
+    dx = torch.empty_like(y)
+    L.check(L.lib().fosvos_relu_bwd(y.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.numel(), L.stream()), "relu_bwd")
+    return dx
+
+
 def taylor_rank(act: torch.Tensor, grad: torch.Tensor, rank: torch.Tensor) -> None:
     """rank (C fp32) += sum over pixels of act * grad / (N H W);  act, grad NHWC of the same dtype."""
     L.require_device(act.device)
@@ -462,3 +561,13 @@ def mask_iou(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     counts = torch.empty((f, 2), dtype=torch.int64, device=a.device)
     L.check(L.lib().fosvos_mask_iou(a.data_ptr(), b.data_ptr(), a.numel() // f, f, counts.data_ptr(), L.stream()), "mask_iou")
     return counts
+
+
+# every launching wrapper runs with its tensors' device current (see _lib.on_tensor_device)
+for _name in ("nchw_to_nhwc", "nhwc_to_nchw", "pack_weight", "pad_bias", "conv3x3", "conv3x3_pool", "conv3x3_pool_only", "conv3x3_side",
+              "conv3x3_wgrad_accumulate", "conv3x3_wgrad_finish", "conv3x3_wgrad", "maxpool2x2", "maxpool2x2_bwd", "side_params_prepare",
+              "side_check_diagonal", "side_fwd", "side_fwd_heads_done", "side_bwd", "bal_loss_fwd", "bal_loss_fwd_bwd",
+              "bal_loss_fwd_bwd_frames", "bal_loss_bwd", "loss_accumulate", "loss_window_finish", "wgrad_fold_all", "repack_all", "sgd_step", "adam_step", "pixel_loss", "taylor_rank", "relu_fwd", "relu_bwd",
+              "ingest_u8", "sigmoid_threshold", "mask_iou"):
+    globals()[_name] = L.on_tensor_device(globals()[_name])
+del _name

@@ -32,6 +32,7 @@ class FusedSGD(Optimizer):
         self._momentum = float(next(iter(moms)))
         self._table = None
         self._table_key = None
+        self._table_gen = 0          # bumps when the device table is REPLACED (captured graphs holding its address go stale)
 
     def _entries(self):
         ent = []
@@ -46,15 +47,33 @@ class FusedSGD(Optimizer):
         return ent
 
     def _ensure_table(self):
+        """(Re)build the device table {param, grad, momentum buffer, lr, weight decay} when any of them changed.  A table
+        of unchanged geometry is rewritten IN PLACE (same device buffers): a captured CUDA graph of the step reads it at
+        replay, so new ``param_groups`` learning rates / weight decays and new momentum buffers (``load_state_dict``) take
+        effect without a re-capture; a different tensor count or size replaces the table and bumps ``_table_gen``."""
+        moms = {g["momentum"] for g in self.param_groups}
+        if len(moms) != 1:
+            raise ValueError("FusedSGD needs one momentum value for all groups")
+        if float(next(iter(moms))) != self._momentum:
+            self._momentum = float(next(iter(moms)))
+            self._table_gen += 1                         # the momentum is a kernel argument: captured steps must be re-captured
         ent = self._entries()
         key = tuple((p.data_ptr(), g.data_ptr(), b.data_ptr(), lr, wd) for p, g, b, lr, wd in ent)
         if key != self._table_key:
             if not ent:
                 self._table = None
+                self._table_gen += 1
             else:
                 dev = ent[0][0].device
                 L.require_device(dev)
-                self._table = ops.sgd_table([(p.detach(), g, b, lr, wd) for p, g, b, lr, wd in ent], dev) + (len(ent),)
+                new = ops.sgd_table([(p.detach(), g, b, lr, wd) for p, g, b, lr, wd in ent], dev) + (len(ent),)
+                old = self._table
+                if old is not None and old[0].numel() == new[0].numel() and old[2] == new[2] and old[3] == new[3] and \
+                        old[0].device == new[0].device and torch.equal(old[1], new[1]):
+                    old[0].copy_(new[0])
+                else:
+                    self._table = new
+                    self._table_gen += 1
             self._table_key = key
         return ent
 
@@ -162,6 +181,11 @@ def _groups(net, mode: str, learning_rate: float, weight_decay: float) -> List[d
         {'params': net.fuse.weight, 'lr': lr / 100, 'weight_decay': wd},
         {'params': net.fuse.bias, 'lr': 2 * lr / 100},
     ]
+    if mode == "offline":
+        # the offline provider also records every group's starting rate (network_provider.py:98-124): schedulers resumed
+        # with last_epoch >= 0 read it
+        for g in groups:
+            g['initial_lr'] = g.get('lr', lr)
     return [g for g in groups if not isinstance(g['params'], list) or len(g['params']) > 0]
 
 

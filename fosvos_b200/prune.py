@@ -105,9 +105,12 @@ class FilterPruner:
         return [(l, i) for l in per_layer for i in per_layer[l]]
 
 
-def prune_convolution(conv: nn.Conv2d, filter_index: int, is_reducing_channels_out: bool, keep_bias: bool = False) -> nn.Conv2d:
-    """Remove one output filter or one input channel (reference ``prune.py:490-514``; like there the new
-    convolution is bias-free unless ``keep_bias``)."""
+def prune_convolution(conv: nn.Conv2d, filter_index: int, is_reducing_channels_out: bool, keep_bias: bool = True) -> nn.Conv2d:
+    """Remove one output filter or one input channel (reference ``prune.py:490-514``).  The reference rebuilds every conv
+    it touches with ``bias=False`` -- its ResNet convs are bias-free and followed by BatchNorm -- which on the VGG topology
+    would delete the trained bias vectors of the pruned conv, of its consumer and of ``side_prep`` for ONE removed filter.
+    So the bias is kept by default here (sliced on out-channel pruning, intact on in-channel pruning);
+    ``keep_bias=False`` is the literal reference surgery, used for the BASELINE configs[2] fixture."""
     d_in, d_out = (0, 1) if is_reducing_channels_out else (1, 0)
     has_bias = keep_bias and conv.bias is not None
     new_conv = nn.Conv2d(conv.in_channels - d_in, conv.out_channels - d_out, kernel_size=conv.kernel_size, stride=conv.stride,
@@ -121,7 +124,7 @@ def prune_convolution(conv: nn.Conv2d, filter_index: int, is_reducing_channels_o
     return new_conv.to(w.device)
 
 
-def prune_vgg_conv_layer(net: OSVOS_VGG, layer_index: int, filter_index: int, keep_bias: bool = False) -> OSVOS_VGG:
+def prune_vgg_conv_layer(net: OSVOS_VGG, layer_index: int, filter_index: int, keep_bias: bool = True) -> OSVOS_VGG:
     """Remove output filter ``filter_index`` of stage conv ``layer_index`` and the matching input channel of its
     consumers (next conv; ``side_prep`` when it is the last conv of stages 1..4)."""
     idx = stage_conv_index(net)
@@ -143,7 +146,7 @@ def prune_vgg_conv_layer(net: OSVOS_VGG, layer_index: int, filter_index: int, ke
 
 
 def prune_step(net: OSVOS_VGG, frames: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], n_filters: int,
-               is_offline: bool = False, keep_bias: bool = False) -> List[Tuple[int, int]]:
+               is_offline: bool = False, keep_bias: bool = True) -> List[Tuple[int, int]]:
     """One pruning iteration of the reference driver (``prune.py`` main loop): rank on the given minibatches,
     normalise, plan, apply.  Returns the applied ``(layer, filter)`` plan."""
     pruner = FilterPruner(net)
@@ -158,7 +161,9 @@ def prune_step(net: OSVOS_VGG, frames: Sequence[torch.Tensor], gts: Sequence[tor
 
 def l2_prune_half(net: OSVOS_VGG, keep_fraction: float = 0.5, keep_bias: bool = False) -> OSVOS_VGG:
     """Deterministic stand-in used by BASELINE configs[2]: keep the ceil(fraction * C) filters of
-    every stage conv with the largest L2 norm."""
+    every stage conv with the largest L2 norm.  ``keep_bias=False`` (the default HERE only) reproduces the reference's
+    literal surgery -- every touched conv, ``side_prep`` included, comes back with ``bias=False`` (prune.py:500) -- which is
+    what SURVEY 8d specifies for this configuration."""
     idx = stage_conv_index(net)
     for layer_index, (si, mi) in enumerate(idx):
         conv = net.stages[si][mi]

@@ -82,3 +82,61 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int 
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+class GradBuckets:
+    """Flat fp32 gradient buffer of a data-parallel trainer, laid out bucket-major in the order the backward pass
+    finishes the layers: bucket k = the convs of stage 4 - k (+ the ``side_prep`` conv hanging off that stage); the last
+    bucket (stage 0) also carries the 1x1 heads (``score_dsn``, ``fuse``).  ``p.grad`` of every parameter is a view into
+    it, so each bucket is ONE contiguous all-reduce with no packing copies (28.6 / 23.6 / 5.9 / 0.9 / 0.15 MB for the full
+    VGG).  The lr = 0 up-sampling weights never carry a gradient and are not part of it."""
+
+    def __init__(self, net, params, device):
+        names = net._grad_names()
+        order = []
+        self.bucket_names = []
+        for k in range(5):
+            si = 4 - k
+            mine = [n for n in names if n.startswith(f"stages.{si}.")]
+            if si > 0:
+                mine += [n for n in names if n.startswith(f"side_prep.{si - 1}.")]
+            if k == 4:
+                mine += [n for n in names if n.startswith(("score_dsn.", "fuse."))]
+            self.bucket_names.append(mine)
+            order += mine
+        missing = [n for n in names if n not in order]
+        if missing:
+            raise RuntimeError(f"GradBuckets: parameters without a bucket: {missing}")
+        self.n_buckets = 5
+        self.flat = torch.zeros(sum(params[n].numel() for n in order), dtype=torch.float32, device=device)
+        self._views = {}
+        self.ranges = []
+        off = 0
+        for mine in self.bucket_names:
+            lo = off
+            for n in mine:
+                p = params[n]
+                self._views[n] = self.flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            self.ranges.append((lo, off))
+        self._fold_tables = {}
+
+    def view(self, name: str) -> torch.Tensor:
+        return self._views[name]
+
+    def fold_table(self, bucket: int, wgrad_ws, grads):
+        """Device table folding this bucket's tensor-core weight-gradient accumulators into its ``.grad`` views."""
+        if bucket not in self._fold_tables:
+            from . import ops
+            ent = [(wgrad_ws[n[:-len(".weight")]], grads[n]) for n in self.bucket_names[bucket]
+                   if wgrad_ws is not None and n.endswith(".weight") and n[:-len(".weight")] in wgrad_ws]
+            self._fold_tables[bucket] = ops.fold_table(ent, self.flat.device) if ent else None
+        return self._fold_tables[bucket]
+
+    def allreduce(self, bucket: int):
+        """Start the sum of one bucket over the ranks on the CURRENT stream's dependency chain; returns the async work
+        handle (None in a single-process run)."""
+        lo, hi = self.ranges[bucket]
+        if hi == lo or not (dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)

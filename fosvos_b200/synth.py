@@ -81,8 +81,15 @@ def make_state_dict(seed: int = 0, kind: str = "random",
     """Reference-layout ``state_dict`` (same keys/order/shapes as
     ``OSVOS_VGG.state_dict()``, reference osvos_vgg.py:50-56) with usable
     random weights.  kind='random': He-normal 3x3 convs, biases U(-0.1,0.1);
-    kind='structured': all-positive, sum-to-one filters (a brightness
-    detector, so logits are bimodal like a trained net's)."""
+    kind='structured': all-positive filters of sum 1.5 (a brightness
+    detector, so logits are bimodal like a trained net's);
+    kind='parent': the same filters with gain 0.3 in the first conv and 1.0
+    elsewhere, so activations stay O(10) at every depth as in a trained
+    parent network -- with 'structured' they grow 2-3x per stage to ~1e4 and
+    the reference's lr = 1e-8 on the sum-reduced loss (train_online.py:81,
+    network_provider.py:144-159) makes the online fine-tune diverge (in the
+    oracle exactly as on the GPU); with 'parent' the loss decreases
+    monotonically.  The fine-tune benchmarks and their parity tests use it."""
     g = torch.Generator().manual_seed(seed)
     widths = _LAY if channels is None else [list(c) for c in channels]
     sd: Dict[str, torch.Tensor] = {}
@@ -99,9 +106,10 @@ def make_state_dict(seed: int = 0, kind: str = "random",
 
     def conv_w(cout, cin):
         w = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (9 * cin))
-        if kind == "structured":
+        if kind in ("structured", "parent"):
             w = w.abs()
-            w = w / w.sum(dim=(1, 2, 3), keepdim=True) * 1.5
+            gain = 1.5 if kind == "structured" else (0.3 if cin == 3 else 1.0)
+            w = w / w.sum(dim=(1, 2, 3), keepdim=True) * gain
         return w
 
     def conv_b(cout):
@@ -121,10 +129,10 @@ def make_state_dict(seed: int = 0, kind: str = "random",
         sd[f"side_prep.{i}.bias"] = conv_b(16)
     for i in range(4):
         w = torch.randn(1, 16, 1, 1, generator=g) * 0.25
-        sd[f"score_dsn.{i}.weight"] = w.abs() if kind == "structured" else w
+        sd[f"score_dsn.{i}.weight"] = w.abs() if kind in ("structured", "parent") else w
         sd[f"score_dsn.{i}.bias"] = torch.zeros(1)
     w = torch.randn(1, 64, 1, 1, generator=g) * 0.125
-    sd["fuse.weight"] = w.abs() if kind == "structured" else w
+    sd["fuse.weight"] = w.abs() if kind in ("structured", "parent") else w
     sd["fuse.bias"] = torch.zeros(1)
     return sd
 

@@ -116,6 +116,21 @@ int fosvos_conv3x3_tc(const void* x, const void* w_packed, const float* bias, co
 int fosvos_conv3x3_tc_pool(const void* x, const void* w_packed, const float* bias, void* y,
                            void* y_pool, int N, int H, int W, int Cin, int Cout, int flags,
                            fosvos_stream_t stream);
+/* (y may be NULL: only the pooled map is written -- inference never reads the full-resolution
+ * output of a stage's last conv when nothing else consumes it, e.g. conv1_2, osvos_vgg.py:63,68.) */
+
+/* side_prep: nn.Conv2d(C, 16, 3, padding=1) with bias and NO ReLU (osvos_vgg.py:42,69) on the tensor
+ * cores with the three taps of a kernel row stacked along GEMM-N (N = 48; conv_side_tc.cu).
+ * w_packed: FOSVOS_W_TC_FWD layout of the (16,Cin,3,3) weight; bias: 16 fp32 or NULL.
+ * y  (N,H,W,16) bf16 or NULL: the side_prep map (needed by the backward pass).
+ * zs (N,H,W) float2 or NULL: {sum_c fuse.w[16i+c] * y[c], sum_c score_dsn.w[c] * y[c] + score_dsn.b} computed
+ *    from the fp32 accumulators -- the two 1x1 heads of the side chain (osvos_vgg.py:75,81) -- with
+ *    heads = params + fosvos_side_params_heads_offset(i) of a prepared side-chain parameter block.
+ * At least one of y / zs is non-NULL.  fosvos_conv3x3_side_tc_supported(Cin): 1 when the layer's
+ * weights fit the kernel's resident shared-memory image (Cin <= 512). */
+int fosvos_conv3x3_side_tc_supported(int Cin);
+int fosvos_conv3x3_side_tc(const void* x, const void* w_packed, const float* bias, void* y, void* zs,
+                           const float* heads, int N, int H, int W, int Cin, fosvos_stream_t stream);
 
 /* weight + bias gradient of the same convolution (autograd convolution_backward,
  * train_online.py:93):  dw[co,ci,r,s] += sum_p x[p+tap,ci] * dz[p,co];  db[co] += sum_p dz[p,co]
@@ -196,6 +211,14 @@ int fosvos_side_fwd(const void* const* sp /*4*/, const int* h /*4*/, const int* 
                     const void* params, float* const* out /*5*/, float* prob, uint8_t* mask,
                     void* workspace, int general, int N, int H, int W, int dtype,
                     fosvos_stream_t stream);
+/* The same as fosvos_side_fwd with general = 0 / 2 when the low-res head maps already sit in `workspace`
+ * (stage after stage, (N,h_i,w_i) float2 each: what fosvos_conv3x3_side_tc writes through `zs`): the heads launch
+ * is skipped and the side_prep maps themselves are not read.  fosvos_side_params_heads_offset(i): float index of
+ * stage i's 36 head parameters {score_dsn.w[16], score_dsn.b, 3 unused, fuse.w[16 i .. 16 i + 15]} in the block. */
+int fosvos_side_params_heads_offset(int stage);
+int fosvos_side_fwd_heads_done(const int* h /*4*/, const int* w /*4*/, const void* params,
+                               float* const* out /*5*/, float* prob, uint8_t* mask, const void* workspace,
+                               int general, int N, int H, int W, fosvos_stream_t stream);
 /* Backward of the chain for upscale weights that are diagonal with one shared k x k kernel per
  * stage (what interp_surgery builds, osvos_layers.py:70-81, and what lr=0 keeps,
  * network_provider.py:154-155).  dout[4] = d fused (required), dout[0..3] = d side maps or NULL.
@@ -237,6 +260,12 @@ int fosvos_bal_loss_fwd_bwd_frames(const float* output, const float* label, long
 int fosvos_bal_loss_bwd(const float* output, const float* label, long long numel, int size_average,
                         const double* stats, const float* grad_out, float grad_scale, float* dx,
                         fosvos_stream_t stream);
+/* Loss bookkeeping of the loops (train_online.py:82,98; train_offline.py:84-88 deep-supervision weighting), on the device:
+ * total[i] = (init ? 0 : total[i]) + (*weight or 1) * part[i], i < n;   then   *loss_sum += sum(total), *last_loss = total[n-1]. */
+int fosvos_loss_accumulate(const float* part, const float* weight, float* total, int n, int init,
+                           fosvos_stream_t stream);
+int fosvos_loss_window_finish(const float* total, int n, float* loss_sum, float* last_loss,
+                              fosvos_stream_t stream);
 
 /* ---- SGD with momentum, multi-tensor (torch.optim.SGD.step, train_online.py:99;
  *      groups: util/network_provider.py:144-159) ---------------------------------------
@@ -306,6 +335,11 @@ int fosvos_adam_step(const fosvos_adam_entry* table, int n_tensors, const long l
 int fosvos_pixel_loss(const float* output, const float* target, long long numel, int kind,
                       int size_average, float grad_scale, float* loss, float* dx,
                       fosvos_stream_t stream);
+/* nn.ReLU(inplace=True) (osvos_vgg.py:93) at module granularity: the stage convs fuse it into their epilogue; these
+ * two serve the introspection path, where a leaf module is called on its own (hooks, prune.py:94-103).
+ * y = max(x, 0);  dx = dy where y > 0 else 0.  fp32, any layout. */
+int fosvos_relu_fwd(const float* x, float* y, long long numel, fosvos_stream_t stream);
+int fosvos_relu_bwd(const float* y, const float* dy, float* dx, long long numel, fosvos_stream_t stream);
 /* Taylor pruning criterion (prune.py:163-178): rank[c] += sum_p act[p,c]*grad[p,c] / (N*H*W). NHWC. */
 int fosvos_taylor_rank(const void* act, const void* grad, float* rank, int N, int H, int W, int CP,
                        int C, int dtype, fosvos_stream_t stream);

@@ -262,17 +262,22 @@ def finetune(sd: Dict[str, torch.Tensor], frame: torch.Tensor, mask: torch.Tenso
     /avg_grad_every_n -> backward -> every n: SGD step + zero_grad.
     ``mode='offline'`` instead follows reference train_offline.py:84-88,102-110
     (five losses, deep-supervision weight (1 - epoch/n_epochs) = 1-epoch_frac).
+    ``frame`` / ``mask`` may be lists with one tensor per iteration (cycled): the train-time augmentation of the
+    reference loader (random flip and Resize scale per sample, dataloaders/custom_transforms.py:63-109) then
+    shows up as frames of different sizes from one iteration to the next.
     Returns (new_state_dict, [loss per iteration before the /n])."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     groups = optimizer_groups(list(params.keys()), mode, learning_rate, weight_decay)
     bufs: Dict[str, Optional[torch.Tensor]] = {k: None for k in params}
     losses, counter = [], 0
-    for _ in range(n_iters):
-        outs = vgg_forward(params, frame)
+    for it in range(n_iters):
+        fr = frame[it % len(frame)] if isinstance(frame, (list, tuple)) else frame
+        mk = mask[it % len(mask)] if isinstance(mask, (list, tuple)) else mask
+        outs = vgg_forward(params, fr)
         if mode == "online":
-            loss = class_balanced_cross_entropy_loss(outs[-1], mask, size_average=False)
+            loss = class_balanced_cross_entropy_loss(outs[-1], mk, size_average=False)
         else:
-            ls = [class_balanced_cross_entropy_loss(o, mask, size_average=False) for o in outs]
+            ls = [class_balanced_cross_entropy_loss(o, mk, size_average=False) for o in outs]
             loss = (1 - epoch_frac) * sum(ls[:-1]) + ls[-1]
         losses.append(float(loss.item()))
         (loss / avg_grad_every_n).backward()

@@ -378,3 +378,49 @@ def test_fused_window_equals_sequential_micro_iterations(precision):
         # (cancelling sums over noise frames: the fp32 summation ORDER differs between the two schedules)
         tol = (2e-3 if precision == "fp32" else 5e-2) * float(d0.abs().max()) + 1e-12
         assert float((d0 - d1).abs().max()) <= tol, (k, float((d0 - d1).abs().max()), float(d0.abs().max()))
+
+
+def test_finetune_480x854_bf16_window_graph_against_oracle():
+    """The configuration bench.py times (BASELINE configs[1]): bf16 tcgen05 kernels + fused 5-frame accumulation window +
+    CUDA graphs + auxiliary-stream overlap at 480x854 -- ten iterations (two optimizer steps) against the CPU oracle's
+    loop of train_online.py:75-101: loss trajectory, weight updates of five named tensors, and the fused probabilities /
+    binarised mask after fine-tuning."""
+    from fosvos_b200.online import OnlineTrainer
+    H, W, n_it = 480, 854, 10
+    x, m = synth.make_frame(0, 0, H, W)
+    xs, ms = synth.make_frame(0, 0, 120, 214)
+    sd = synth.calibrate(synth.make_state_dict(0, "parent"), O.vgg_forward, xs, mask=ms)      # bench.py's weights
+    torch.set_num_threads(os.cpu_count())
+    ref_sd, ref_losses = O.finetune(sd, x, m, n_it, 5)
+    net = _net(sd, "bf16")
+    tr = OnlineTrainer(net, H, W, 5, FB.get_optimizer_online(net), use_graph=True, fuse_window=True)
+    assert tr.use_graph and tr.fuse
+    tr.set_frame(x.to(DEV), m.to(DEV))
+    losses = []
+    tr.run(n_it, losses)
+    assert tr._window_graph is not None                                  # the replayed path, not an eager one
+    assert len(losses) == n_it
+    rel = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+    print("loss max rel err", rel, "losses", ref_losses)
+    assert rel <= 1e-2, (losses, ref_losses)
+    assert ref_losses[-1] < ref_losses[0]                                # the fine-tune converges on these weights
+    mine = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    for k in ["stages.0.0.weight", "stages.2.3.weight", "stages.4.5.weight", "side_prep.3.weight", "fuse.weight"]:
+        d, dr = (mine[k] - sd[k]).double(), (ref_sd[k] - sd[k]).double()
+        assert float(dr.abs().max()) > 0
+        cos = float((d * dr).sum() / (d.norm() * dr.norm()))
+        rl2 = float((d - dr).norm() / dr.norm())
+        print(k, "update cos", cos, "rel_l2", rl2)
+        # bf16 activations / gradients: the update direction is held norm-wise (heads tightly)
+        assert cos >= (0.999 if k.startswith(("fuse", "side_prep")) else 0.98), (k, cos, rl2)
+        assert rl2 <= (0.05 if k.startswith(("fuse", "side_prep")) else 0.2), (k, cos, rl2)
+    for k in sd:
+        if k.startswith(("score_dsn", "upscale")):
+            assert torch.equal(mine[k], sd[k]), k
+    with torch.no_grad():
+        ref = O.vgg_forward(ref_sd, x)
+    outs, prob, mask = net.predict(x.to(DEV))
+    err = float((prob.cpu() - O.probabilities(ref[4])).abs().max())
+    print("post-fine-tune max|dprob|", err)
+    assert err <= TOL_PROB["bf16"], err
+    assert _iou(mask.cpu(), O.binarise(O.probabilities(ref[4]))) >= 0.995
