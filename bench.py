@@ -236,12 +236,28 @@ def run_ours(args):
             extras["parity"] = parity_check(net, trainer, sd0, frames_d, masks_d, frames_h, args, losses_ours)
         if args.gpu_reference:
             extras["gpu_reference"] = gpu_reference(sd0, frames_d, masks_d, args, job_s)
+    # ---- BASELINE configs[3] and configs[4]: the multi-GPU pipelines (every rank takes part) --------------------------
+    if args.config4:
+        extras["config4"] = config4_leg(args, rank, world, dev, sd_dev, trainer, net)
+    if args.config5 and world > 1:
+        extras["config5"] = config5_leg(args, rank, world, dev, sd0, frames_d, masks_d)
     if rank == 0:
         # ---- roofline of the dominant kernel family (3x3 conv implicit GEMM), measured live -------
         roof = conv_roofline(new_net(), frames_d[:args.batch], peaks, args.precision)
         side = side_roofline(new_net(), frames_d[:args.batch], peaks)
         loss_roof = loss_roofline(args.batch, dev, peaks)
         cpu = cpu_baseline(sd0, frames_h, masks_h, args) if world == 1 else None
+        if world == 1:
+            extras["roofline_wgrad"], extras["roofline_dgrad"] = backward_rooflines(new_net(), frames_d, peaks, args.avg_grad_every_n)
+            if args.config3:
+                extras["config3"] = config3_leg(sd0, frames_d, frames_h, peaks, dev)
+        ft_tflops = ITER_GFLOP * args.iters * args.steps / (t_ft_max / 1e3) / 1e3 if t_ft_max > 0 else None
+        if ft_tflops:
+            extras["roofline_step"] = dict(bound="tensor", kernel="one fine-tune step: fused 5-iteration window (forward, loss, backward) + optimizer step, as timed in `value`",
+                                           achieved=ft_tflops, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ft_tflops / peaks["bf16_tflops"],
+                                           frac_of_sustained=ft_tflops / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
+                                           traffic=None, peak_source=peaks["source"] + " burst (sustained beside it: the step runs for 0.4 s under the power cap)",
+                                           gflop_per_iteration=ITER_GFLOP, ms_per_iteration=t_ft_max / args.steps / args.iters)
         out = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -291,49 +307,170 @@ def _time_ms(fn, reps=5):
     return best
 
 
+def _conv_flops(conv, h, w, n):
+    return 2.0 * conv.in_channels * conv.out_channels * 9 * h * w * n / 1e9
+
+
 def conv_roofline(net, frames, peaks, precision):
-    """Achieved TFLOP/s of the 17 conv3x3 launches of a forward pass (CUDA events around exactly
-    those launches, current stream), vs the measured dense bf16 peak."""
+    """Achieved TFLOP/s of the 17 conv3x3 launches of an INFERENCE forward pass exactly as the network issues them (first
+    layer c8; conv1_2 pool-only; last conv of stages 1-3 with the fused pool; side_prep through the row-stacked kernel
+    with the heads in its epilogue): CUDA events around exactly those launches on the launching stream, vs the measured
+    dense bf16 peak."""
     from fosvos_b200 import _lib as L, ops
     from fosvos_b200.networks import _act_dtype
     n = frames.shape[0]
     dt = _act_dtype(precision)
     impl = net._impl()
+    tc = impl == "tc"
+    RB = L.CONV_BIAS | L.CONV_RELU
     with torch.no_grad():
+        params = net._side()
+        heads = ops.side_heads_views(params)
         a = ops.nchw_to_nhwc(frames, dt)
-        plan = []
+        plan = []                       # (callable, conv, h, w, kind)
+        stage_convs = net._stage_convs()
+        for si, convs in enumerate(stage_convs):
+            if si > 0:
+                a = ops.maxpool2x2(a)
+            for ci, conv in enumerate(convs):
+                pc = net._packed_for(conv, False)
+                cp = ops.pad8(conv.out_channels)
+                x = a
+                last = ci == len(convs) - 1
+                if tc and last and si == 0 and net.fuse_pool:
+                    plan.append((lambda x=x, pc=pc, cp=cp: ops.conv3x3_pool_only(x, pc.w_fwd, pc.bias, cp, RB), conv, x.shape[1], x.shape[2], "pool-only"))
+                elif tc and last and si < 4 and net.fuse_pool:
+                    plan.append((lambda x=x, pc=pc, cp=cp: ops.conv3x3_pool(x, pc.w_fwd, pc.bias, cp, RB), conv, x.shape[1], x.shape[2], "conv+pool"))
+                else:
+                    o = torch.empty((x.shape[0], x.shape[1], x.shape[2], cp), dtype=x.dtype, device=x.device)
+                    plan.append((lambda x=x, pc=pc, cp=cp, o=o: ops.conv3x3(x, pc.w_fwd, pc.bias, cp, RB, out=o, impl=impl), conv, x.shape[1], x.shape[2], "conv"))
+                a = ops.conv3x3(a, pc.w_fwd, pc.bias, cp, RB, impl=impl)
+            if si > 0:
+                sp_conv = net.side_prep[si - 1]
+                pc = net._packed_for(sp_conv, False)
+                x = a
+                if tc and net.side_tc and ops.side_tc_supported(x.shape[3]):
+                    zs = torch.empty((x.shape[0] * x.shape[1] * x.shape[2], 2), dtype=torch.float32, device=x.device)
+                    plan.append((lambda x=x, pc=pc, zs=zs, hv=heads[si - 1]: ops.conv3x3_side(x, pc.w_fwd, pc.bias, zs=zs, heads=hv, want_y=False),
+                                 sp_conv, x.shape[1], x.shape[2], "side_prep row-stacked + heads"))
+                else:
+                    o = torch.empty((x.shape[0], x.shape[1], x.shape[2], 16), dtype=x.dtype, device=x.device)
+                    plan.append((lambda x=x, pc=pc, o=o: ops.conv3x3(x, pc.w_fwd, pc.bias, 16, L.CONV_BIAS, out=o, impl=impl), sp_conv, x.shape[1], x.shape[2], "side_prep"))
+
+        def run():
+            for fn, *_ in plan:
+                fn()
+        ms = _time_ms(run)
+        per_layer = []
+        for fn, conv, h, w, kind in plan:
+            t = _time_ms(fn, reps=3)
+            per_layer.append(dict(cin=conv.in_channels, cout=conv.out_channels, hw=[h, w], kind=kind, ms=round(t, 4),
+                                  tflops=round(_conv_flops(conv, h, w, n) / t, 1)))
+    gflop = sum(_conv_flops(conv, h, w, n) for _, conv, h, w, _ in plan)
+    achieved = gflop / ms                             # GFLOP / ms = TFLOP/s
+    peak = peaks["bf16_tflops"]
+    # DRAM bytes of the same launches from the committed ncu --set full capture (only if it was taken at this batch)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r02_conv_forward_traffic.json")
+    if tc and os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("batch") == n:
+            traffic, traffic_src = tj["traffic_bytes"], "profiles/r02_conv_forward_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the 17 launches of one batch-%d forward)" % n
+    return dict(bound="tensor", kernel="conv3x3_tc_kernel + conv3x3_side_tc_kernel (17 launches = one inference forward pass)" if tc else "conv3x3_simt_kernel",
+                achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
+                peak_source=peaks["source"] + " burst", batch=n, gflop_per_frame=gflop / n, ms_per_forward_convs=ms, per_layer=per_layer)
+
+
+def backward_rooflines(net, frames, peaks, n_window):
+    """Weight-gradient and data-gradient kernels at the fine-tune window's batch (CUDA events around exactly those launches):
+    17 tensor-core weight gradients (258.23 GFLOP per frame) and 16 data gradients (256.81: the first conv needs none)."""
+    from fosvos_b200 import _lib as L, ops
+    from fosvos_b200.networks import _act_dtype
+    if net._impl() != "tc":
+        return None, None
+    n = n_window
+    g = torch.Generator(device=frames.device).manual_seed(3)
+    with torch.no_grad():
+        a = ops.nchw_to_nhwc(frames[:1].expand(n, -1, -1, -1).contiguous(), torch.bfloat16)
+        wg, dg = [], []
         for si, convs in enumerate(net._stage_convs()):
             if si > 0:
                 a = ops.maxpool2x2(a)
-            for conv in convs:
-                pc = net._packed_for(conv, False)
-                plan.append((a, pc, ops.pad8(conv.out_channels), L.CONV_BIAS | L.CONV_RELU, conv))
-                a = ops.conv3x3(a, pc.w_fwd, pc.bias, ops.pad8(conv.out_channels), L.CONV_BIAS | L.CONV_RELU, impl=impl)
+            for ci, conv in enumerate(convs):
+                pc = net._packed_for(conv, True)
+                cp = ops.pad8(conv.out_channels)
+                x = a
+                a = ops.conv3x3(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU)
+                dz = (torch.randn(a.shape, device=a.device, generator=g) * 0.01).to(torch.bfloat16)
+                ws = ops.wgrad_workspace(x.shape[3], cp, a.device)
+                db = torch.zeros(conv.out_channels, device=a.device)
+                wg.append((lambda x=x, dz=dz, ws=ws, db=db, co=conv.out_channels: ops.conv3x3_wgrad_accumulate(x, dz, ws, db, co), conv, x.shape[1], x.shape[2]))
+                if not (si == 0 and ci == 0):
+                    o = torch.empty_like(x)
+                    dg.append((lambda x=x, dz=dz, pc=pc, o=o: ops.conv3x3(dz, pc.w_dgrad, None, x.shape[3], L.CONV_MASK, mask=x, out=o), conv, x.shape[1], x.shape[2]))
             if si > 0:
-                pc = net._packed_for(net.side_prep[si - 1], False)
-                plan.append((a, pc, 16, L.CONV_BIAS, net.side_prep[si - 1]))
-        outs = [torch.empty((x.shape[0], x.shape[1], x.shape[2], cp), dtype=x.dtype, device=x.device) for x, _, cp, _, _ in plan]
-        def run():
-            for (x, pc, cp, fl, _), o in zip(plan, outs):
-                ops.conv3x3(x, pc.w_fwd, pc.bias, cp, fl, out=o, impl=impl)
-        ms = _time_ms(run)
-        per_layer = []
-        for (x, pc, cp, fl, conv), o in zip(plan, outs):
-            t = _time_ms(lambda: ops.conv3x3(x, pc.w_fwd, pc.bias, cp, fl, out=o, impl=impl), reps=3)
-            gf = 2.0 * conv.in_channels * conv.out_channels * 9 * x.shape[1] * x.shape[2] * n / 1e9
-            per_layer.append(dict(cin=conv.in_channels, cout=conv.out_channels, hw=[x.shape[1], x.shape[2]], ms=round(t, 4), tflops=round(gf / t, 1)))
-    achieved = FWD_GFLOP * n / ms                     # GFLOP / ms = TFLOP/s
-    peak = peaks["bf16_tflops"]
-    # DRAM bytes of the same 17 launches from the committed ncu --set full capture (only if it was taken at this batch)
-    traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01h_conv_forward_traffic.json")
-    if impl == "tc" and os.path.exists(tp):
-        tj = json.load(open(tp))
-        if tj.get("batch") == n:
-            traffic, traffic_src = tj["traffic_bytes"], "profiles/r01h_conv_forward_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the 17 launches of one batch-%d forward)" % n
-    return dict(bound="tensor", kernel="conv3x3_tc_kernel (17 launches = one forward pass)" if impl == "tc" else "conv3x3_simt_kernel",
-                achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
-                peak_source=peaks["source"] + " burst", batch=n, ms_per_forward_convs=ms, per_layer=per_layer)
+                sp_conv = net.side_prep[si - 1]
+                pc = net._packed_for(sp_conv, True)
+                x = a
+                dz = (torch.randn((a.shape[0], a.shape[1], a.shape[2], 16), device=a.device, generator=g) * 0.01).to(torch.bfloat16)
+                ws = ops.wgrad_workspace(x.shape[3], 16, a.device)
+                db = torch.zeros(16, device=a.device)
+                wg.append((lambda x=x, dz=dz, ws=ws, db=db: ops.conv3x3_wgrad_accumulate(x, dz, ws, db, 16), sp_conv, x.shape[1], x.shape[2]))
+                o = torch.empty_like(x)
+                dg.append((lambda x=x, dz=dz, pc=pc, o=o: ops.conv3x3(dz, pc.w_dgrad, None, x.shape[3], L.CONV_MASK, mask=x, out=o), sp_conv, x.shape[1], x.shape[2]))
+        out = []
+        for name, plan in (("conv3x3_wgrad_tc_kernel (17 launches = the weight gradients of one window)", wg),
+                           ("conv3x3_tc_kernel, data-gradient use (16 launches = the data gradients of one window)", dg)):
+            ms = _time_ms(lambda: [fn() for fn, *_ in plan], reps=3)
+            gflop = sum(_conv_flops(c, h, w, n) for _, c, h, w in plan)
+            per_layer = [dict(cin=c.in_channels, cout=c.out_channels, hw=[h, w], ms=round(_time_ms(fn, reps=3), 4)) for fn, c, h, w in plan]
+            for d, (_, c, h, w) in zip(per_layer, plan):
+                d["tflops"] = round(_conv_flops(c, h, w, n) / d["ms"], 1)
+            out.append(dict(bound="tensor", kernel=name, achieved=gflop / ms, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=gflop / ms / peaks["bf16_tflops"],
+                            traffic=None, peak_source=peaks["source"] + " burst", batch=n, gflop_per_frame=gflop / n, ms=ms, per_layer=per_layer))
+    return out[0], out[1]
+
+
+def config3_leg(sd0, frames_d, frames_h, peaks, dev, batch=32, reps=3):
+    """BASELINE configs[2]: channel-pruned VGG (50 % of the filters of every stage conv: prune.l2_prune_half, the reference's
+    literal bias-free surgery prune.py:490-514), batched bf16 inference, batch 32 at 480x854: frames/s, the conv roofline
+    with FLOPs recomputed from the actual channel table, parity of one frame of the batch against the CPU oracle (and the
+    reference's own bf16 loss on the same weights next to it)."""
+    import fosvos_b200 as FB
+    from fosvos_b200 import prune as P
+    from oracle import osvos_oracle as O
+    net = FB.OSVOS_VGG(pretrained=0)
+    net.load_state_dict(sd0)
+    net = net.to(dev)
+    net.precision = "bf16"
+    P.l2_prune_half(net, 0.5)
+    psd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    fb = frames_d[:batch]
+    with torch.no_grad():
+        for _ in range(3):
+            net.predict(fb)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            _, prob, mask = net.predict(fb)
+        e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    roof = conv_roofline(net, fb, peaks, "bf16")
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = O.vgg_forward(psd, frames_h[0:1])
+        ctx, prep = _oracle_on_gpu("bf16_autocast")
+        with ctx():
+            o16 = O.vgg_forward({k: v.to(dev) for k, v in psd.items()}, frames_d[0:1])
+    pr = O.probabilities(ref[4])
+    i_, u_ = O.mask_iou_counts(mask[0:1].cpu(), O.binarise(pr))
+    channels = [m.out_channels for st in net._stage_convs() for m in st]
+    return dict(workload=f"configs[2]: l2_prune_half(0.5) of the parent weights, batch {batch} x 480x854, bf16 (predict: ingest -> 5 maps + prob + mask)",
+                channels=channels, params=int(sum(p.numel() for p in net.parameters())), frames_per_s=batch / (ms / 1e3), ms_per_batch=ms,
+                roofline={k: v for k, v in roof.items() if k != "per_layer"}, per_layer=roof["per_layer"],
+                parity=dict(frame=0, max_dprob=float((prob[0:1].cpu() - pr).abs().max()), iou=1.0 if u_ == 0 else i_ / u_,
+                            reference_under_autocast_max_dprob=float((torch.sigmoid(o16[4].float().cpu()) - pr).abs().max())))
 
 
 def side_roofline(net, frames, peaks):
@@ -558,6 +695,76 @@ def parity_check(net, trainer, sd0, frames_d, masks_d, frames_h, args, losses_ou
     return res
 
 
+def config4_leg(args, rank, world, dev, sd_dev, trainer, net, n_sequences=20):
+    """BASELINE configs[3]: the DAVIS-2016-val-shaped pipeline -- 20 synthetic sequences x `args.frames` frames, per-sequence
+    fine-tune + inference, sequence i on rank i % world (train_online.py:184-186), no collective.  Every rank works through
+    its sequences back to back on its resident trainer; wall = max over ranks of the device time."""
+    from fosvos_b200 import sharding
+    from fosvos_b200.online import sequences_for_rank
+    mine = sequences_for_rank(list(range(n_sequences)), rank, world)
+    data = [make_sequence_gpu(q, args.frames) for q in mine]
+    data = [(f.to(dev), m.to(dev)) for f, m in data]
+    sharding.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for frames, masks in data:
+        trainer.reset(sd_dev)
+        trainer.set_frame(frames[0:1], masks[0:1])
+        trainer.run(args.iters)
+        for i in range(0, args.frames, args.batch):
+            net.predict(frames[i:i + args.batch])
+    e1.record(); torch.cuda.synchronize(); sharding.barrier()
+    t = e0.elapsed_time(e1) / 1e3
+    t_max, t_sum = sharding.max_over_ranks(t), sharding.sum_over_ranks(t)
+    t_min = -sharding.max_over_ranks(-t)
+    per_rank = [len(sequences_for_rank(list(range(n_sequences)), r, world)) for r in range(world)]
+    return dict(workload=f"configs[3]: {n_sequences} sequences x {args.frames} frames, fine-tune ({args.iters} it) + inference per sequence, sequence i -> rank i % {world}",
+                wall_s=t_max, frames_per_s=n_sequences * args.frames / t_max, s_per_sequence=t_sum / n_sequences,
+                sequences_per_rank=per_rank, ideal_speedup=n_sequences / max(per_rank), rank_time_s_min_max=[t_min, t_max],
+                tail_imbalance=t_max / max(t_min, 1e-9), collective="none",
+                note="the optimizer steps of a sequence are sequential, so a tail sequence cannot be spread over the ranks that finished; splitting "
+                     "only its inference (4 % of a sequence job) over idle ranks would need a 61 MB weight broadcast for a < 1 % gain")
+
+
+def config5_leg(args, rank, world, dev, sd0, frames_d, masks_d, windows=6):
+    """BASELINE configs[4]: offline parent training, data parallel -- every rank runs 5 micro-iterations (one fused window) on
+    its own frames with the 5-map deep-supervision loss (train_offline.py:84-88) and the offline param groups
+    (network_provider.py:98-125); gradients are summed over the ranks (61 MB fp32 per optimizer step) before the fused SGD
+    step.  Three schedules are timed on the device (max over ranks): no exchange (the floor), ONE flat all-reduce after the
+    backward pass, and per-stage buckets all-reduced on a side stream while the backward pass continues."""
+    import fosvos_b200 as FB
+    from fosvos_b200 import sharding
+    from fosvos_b200.online import OnlineTrainer
+    n_local = args.avg_grad_every_n
+    res = {}
+    for name, dp, overlap in (("no_exchange", False, False), ("flat_allreduce", True, False), ("bucketed_overlapped", True, True)):
+        net = FB.OSVOS_VGG(pretrained=0)
+        net.load_state_dict(sd0)
+        net = net.to(dev)
+        net.precision = args.precision
+        tr = OnlineTrainer(net, H, W, n_local * (world if dp else 1), FB.get_optimizer_offline(net), use_graph=True, deep_supervision=0.5,
+                           data_parallel=dp, world_size=world, fuse_window=True, overlap_allreduce=overlap)
+        idx = [(rank * n_local + j) % frames_d.shape[0] for j in range(n_local)]
+        tr.set_frames(frames_d[idx], masks_d[idx])
+        tr.run(2 * n_local)                                   # warm-up: capture, NCCL channels
+        sharding.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); tr.run(windows * n_local); e1.record(); torch.cuda.synchronize(); sharding.barrier()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1)) / windows
+        res[name] = dict(ms_per_optimizer_step=ms, micro_iterations_per_s=world * n_local / (ms / 1e3))
+        del tr, net
+        torch.cuda.empty_cache()
+    base = res["no_exchange"]["ms_per_optimizer_step"]
+    for k in ("flat_allreduce", "bucketed_overlapped"):
+        res[k]["exposed_allreduce_ms"] = res[k]["ms_per_optimizer_step"] - base
+        res[k]["exposed_allreduce_frac_of_step"] = (res[k]["ms_per_optimizer_step"] - base) / res[k]["ms_per_optimizer_step"]
+    res["workload"] = (f"configs[4]: data-parallel offline parent training at 480x854, deep supervision (5 losses), offline param groups, "
+                       f"{n_local} micro-iterations per rank and optimizer step (global accumulation {n_local * world}), NCCL all-reduce of the fp32 gradients")
+    res["allreduce_bytes_per_step"] = 4 * sum(p.numel() for n_, p in FB.OSVOS_VGG(pretrained=0).named_parameters() if not n_.startswith("upscale"))
+    res["scaling"] = "weak (per-rank work fixed)"
+    return res
+
+
 def cpu_baseline(sd, frames, masks, args, forward_frames=2, ft_iters=1):
     """The oracle port of the reference path on the host cores, bounded sample, extrapolated."""
     from oracle import osvos_oracle as O
@@ -631,6 +838,9 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--fuse-window", type=int, default=1,
                     help="run the avg_grad_every_n micro-iterations between two optimizer steps as one batched pass (same gradients)")
+    ap.add_argument("--config3", type=int, default=1, help="N=1: BASELINE configs[2] line (pruned 50 %, batch 32, bf16)")
+    ap.add_argument("--config4", type=int, default=1, help="BASELINE configs[3] leg: 20 sequences sharded by sequence over the ranks")
+    ap.add_argument("--config5", type=int, default=1, help="N>1: BASELINE configs[4] leg: data-parallel offline step with the gradient all-reduce")
     ap.add_argument("--parity", type=int, default=1, help="N=1: run the benchmarked job on the on-box oracle too and compare (adds ~1 min)")
     ap.add_argument("--gpu-reference", type=int, default=1, help="N=1: time the reference arithmetic under stock PyTorch/cuDNN on this GPU")
     args = ap.parse_args()

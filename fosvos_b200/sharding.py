@@ -88,7 +88,7 @@ class GradBuckets:
     """Flat fp32 gradient buffer of a data-parallel trainer, laid out bucket-major in the order the backward pass
     finishes the layers: bucket k = the convs of stage 4 - k (+ the ``side_prep`` conv hanging off that stage); the last
     bucket (stage 0) also carries the 1x1 heads (``score_dsn``, ``fuse``).  ``p.grad`` of every parameter is a view into
-    it, so each bucket is ONE contiguous all-reduce with no packing copies (28.6 / 23.6 / 5.9 / 0.9 / 0.15 MB for the full
+    it, so each bucket is ONE contiguous all-reduce with no packing copies (28.6 / 23.9 / 6.0 / 1.0 / 0.2 MB for the full
     VGG).  The lr = 0 up-sampling weights never carry a gradient and are not part of it."""
 
     def __init__(self, net, params, device):

@@ -145,7 +145,10 @@ def test_prune_plan_and_surgery_keep_the_function_of_survivors():
     # bf16 tensor-core path on the ragged channel counts
     net.precision = "bf16"
     outs_b = net.forward(x.to(DEV))
-    assert float((torch.sigmoid(outs_b[4].cpu()) - torch.sigmoid(ref[4])).abs().max()) <= 4e-2
+    from conftest import bf16_budget
+    assert float((torch.sigmoid(outs_b[4].cpu()) - torch.sigmoid(ref[4])).abs().max()) <= bf16_budget(new_sd, x, ref)
+    # the VGG surgery keeps the trained biases (sliced on out-channel pruning); bias-free convs are the explicit opt-in
+    assert all(c.bias is not None and c.bias.shape[0] == c.out_channels for c in convs) and net.side_prep[0].bias is not None
 
 
 def test_l2_prune_half_builds_the_config3_network():
@@ -159,7 +162,9 @@ def test_l2_prune_half_builds_the_config3_network():
     new_sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     with torch.no_grad():
         ref = O.vgg_forward(new_sd, x)
-    assert float((torch.sigmoid(outs[4].cpu()) - torch.sigmoid(ref[4])).abs().max()) <= 4e-2
+    from conftest import bf16_budget
+    # noise frames through a pruned structured net: held to the reference's own bf16 loss on the same weights and input
+    assert float((torch.sigmoid(outs[4].detach().cpu()) - torch.sigmoid(ref[4])).abs().max()) <= bf16_budget(new_sd, x, ref)
 
 
 @pytest.mark.parametrize("criterion", ["MSE", "L1", "CBCEL"])

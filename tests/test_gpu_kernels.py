@@ -128,6 +128,101 @@ def test_conv3x3_fused_maxpool(case):
     assert torch.equal(yp, p_ref)
 
 
+@pytest.mark.parametrize("case", [(1, 33, 45, 64, 64), (2, 16, 24, 64, 128), (1, 9, 17, 40, 72)])
+def test_conv3x3_pool_only(case):
+    """Inference form of the fused pool: the full-resolution output is not written at all (y = NULL); the pooled map is
+    bit-identical to the one written next to the full output."""
+    n, h, w_, cin, cout = case
+    g = _gen(52)
+    x = _nhwc(torch.randn(n, cin, h, w_, generator=g), torch.bfloat16)
+    wp = ops.pack_weight(torch.randn(cout, cin, 3, 3, generator=g).to(DEV) * 0.05, L.W_TC_FWD, torch.bfloat16)
+    bp = ops.pad_bias(torch.randn(cout, generator=g).to(DEV), cout, DEV)
+    cp = ops.pad8(cout)
+    _, p_ref = ops.conv3x3_pool(x, wp, bp, cp, L.CONV_BIAS | L.CONV_RELU)
+    yp = ops.conv3x3_pool_only(x, wp, bp, cp, L.CONV_BIAS | L.CONV_RELU)
+    assert torch.equal(yp, p_ref)
+
+
+SIDE_CASES = [
+    # N, H, W, Cin: tile = 30 x 4 outputs; widths around the tile edge, one-pixel maps, ragged channel counts (pruned nets)
+    (1, 30, 54, 512), (2, 15, 27, 512), (1, 45, 70, 128), (3, 7, 5, 64), (1, 4, 30, 256), (1, 5, 31, 128), (1, 3, 29, 64),
+    (1, 1, 1, 64), (2, 9, 61, 104), (1, 12, 33, 520), (1, 8, 16, 8),
+]
+
+
+@pytest.mark.parametrize("case", SIDE_CASES)
+@pytest.mark.parametrize("heads", [False, True])
+def test_conv3x3_side_tc(case, heads):
+    """side_prep (C -> 16, bias, no ReLU; osvos_vgg.py:42,69) through the row-stacked kernel (conv_side_tc.cu) against exact
+    accumulation over the same bf16 operands, and against the generic tcgen05 kernel; with ``heads`` the two 1x1 heads
+    (score_dsn, this stage's fuse columns; osvos_vgg.py:75,81) come out of the same epilogue from the fp32 accumulators."""
+    n, h, w_, cin = case
+    g = _gen(hash(case) % 1000 + 7)
+    x = torch.randn(n, cin, h, w_, generator=g)
+    w = torch.randn(16, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(16, generator=g)
+    xd = _nhwc(x, torch.bfloat16)
+    assert ops.side_tc_supported(xd.shape[3])
+    wp = ops.pack_weight(w.to(DEV), L.W_TC_FWD, torch.bfloat16)
+    bp = ops.pad_bias(b.to(DEV), 16, DEV)
+    ref = _conv_ref(_bf16r(x), _bf16r(w), b, False)                       # fp32 result of exact accumulation
+    zs = hp = None
+    if heads:
+        hp = torch.randn(36, generator=g).to(DEV)                          # score.w[16], score.b, 3 unused, fuse.w[16]
+        zs = torch.full((n * h * w_, 2), float("nan"), device=DEV)
+    y = ops.conv3x3_side(xd, wp, bp, zs=zs, heads=hp)
+    torch.cuda.synchronize()
+    got = _nchw(y, 16)
+    assert torch.allclose(got, ref, rtol=2 ** -7, atol=2e-2), float((got - ref).abs().max())
+    y_gen = ops.conv3x3(xd, wp, bp, 16, L.CONV_BIAS)                       # same operands, other summation order
+    assert torch.allclose(y.float(), y_gen.float(), rtol=2 ** -7, atol=1e-2)
+    if heads:
+        hpc = hp.cpu()
+        z_ref = (ref * hpc[20:36].view(1, 16, 1, 1)).sum(1)
+        s_ref = (ref * hpc[0:16].view(1, 16, 1, 1)).sum(1) + hpc[16]
+        got_z = zs.cpu().view(n, h, w_, 2)
+        assert torch.allclose(got_z[..., 0], z_ref, rtol=1e-4, atol=1e-3), float((got_z[..., 0] - z_ref).abs().max())
+        assert torch.allclose(got_z[..., 1], s_ref, rtol=1e-4, atol=1e-3), float((got_z[..., 1] - s_ref).abs().max())
+        # heads only (inference): the 16-channel map itself is not written
+        zs2 = torch.full_like(zs, float("nan"))
+        assert ops.conv3x3_side(xd, wp, bp, zs=zs2, heads=hp, want_y=False) is None
+        assert torch.equal(zs2, zs)
+
+
+def test_side_fwd_from_fused_heads_matches_heads_kernel():
+    """fosvos_side_fwd_heads_done on head maps written by the conv epilogue == fosvos_side_fwd on the 16-channel maps
+    (up to the bf16 rounding of those maps, which the fused path skips)."""
+    g = _gen(77)
+    n, H, W = 2, 45, 70
+    hs, ws, h_, w_ = [], [], H, W
+    for _ in range(4):
+        h_, w_ = (h_ + 1) // 2, (w_ + 1) // 2
+        hs.append(h_); ws.append(w_)
+    up = [O.interp_surgery_weight(16, 4 << i).to(DEV) for i in range(4)]
+    up1 = [O.interp_surgery_weight(1, 4 << i).to(DEV) for i in range(4)]
+    sw = [(torch.randn(1, 16, 1, 1, generator=g) * 0.2).to(DEV) for _ in range(4)]
+    sb = [torch.randn(1, generator=g).to(DEV) for _ in range(4)]
+    fw, fb = (torch.randn(1, 64, 1, 1, generator=g) * 0.1).to(DEV), torch.randn(1, generator=g).to(DEV)
+    params = ops.side_params_prepare(up, up1, sw, sb, fw, fb)
+    assert ops.side_separable(params)
+    heads = ops.side_heads_views(params)
+    zs_flat, zs_views = ops.side_zs_workspace(n, hs, ws, DEV)
+    sps = []
+    for i, cin in enumerate([128, 256, 512, 512]):
+        x = _nhwc(torch.randn(n, cin, hs[i], ws[i], generator=g), torch.bfloat16)
+        wp = ops.pack_weight((torch.randn(16, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5).to(DEV), L.W_TC_FWD, torch.bfloat16)
+        bp = ops.pad_bias(torch.randn(16, generator=g).to(DEV), 16, DEV)
+        sps.append(ops.conv3x3_side(x, wp, bp, zs=zs_views[i], heads=heads[i]))
+    outs_a, prob_a, mask_a = ops.side_fwd(sps, params, H, W, general=2, want_prob=True, want_mask=True)
+    outs_b, prob_b, mask_b = ops.side_fwd_heads_done(zs_flat, hs, ws, params, n, H, W, general=2, want_prob=True, want_mask=True)
+    for a, b in zip(outs_a, outs_b):
+        assert torch.allclose(a, b, rtol=1e-2, atol=3e-2), float((a - b).abs().max())
+    assert torch.equal(mask_b.cpu(), O.binarise(prob_b.cpu()))
+    outs_c, _, _ = ops.side_fwd_heads_done(zs_flat, hs, ws, params, n, H, W, general=0)
+    for b, c in zip(outs_b, outs_c):
+        assert torch.allclose(b, c, rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("impl,dt", [("simt", torch.float32), ("tc", torch.bfloat16)])
 def test_conv3x3_mask_accumulate_dgrad(impl, dt):
     """The data-gradient use of the kernel: flipped/transposed weights, ReLU mask, += fan-in."""

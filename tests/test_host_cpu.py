@@ -187,6 +187,16 @@ def test_bench_sharding_two_ranks_gloo(tmp_path):
         "for i, p in enumerate(ps[:3]): p.grad = torch.full_like(p, float((i + 1) * (rank + 1)))\n"
         "allreduce_gradients(ps, bucket_bytes=1024)       # three gradients in two buckets, one parameter without a gradient\n"
         "assert all(torch.equal(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(ps[:3])) and ps[3].grad is None\n"
+        "# bucketed exchange of the data-parallel trainer: per-stage buckets, p.grad are views, async all-reduce per bucket\n"
+        "import fosvos_b200 as FB\n"
+        "from fosvos_b200.sharding import GradBuckets\n"
+        "net = FB.OSVOS_VGG(pretrained=0)\n"
+        "params = dict(net.named_parameters())\n"
+        "bk = GradBuckets(net, params, 'cpu')\n"
+        "for k, name in enumerate(net._grad_names()): bk.view(name).fill_(float((k % 7 + 1) * (rank + 1)))\n"
+        "works = [bk.allreduce(b) for b in range(bk.n_buckets)]\n"
+        "for w in works: w.wait()\n"
+        "for k, name in enumerate(net._grad_names()): assert torch.equal(bk.view(name), torch.full_like(params[name], 3.0 * (k % 7 + 1))), name\n"
         "open(os.path.join(os.path.dirname(__file__), f'rank{rank}.txt'), 'w').write(repr(mine))\n"
         "dist.destroy_process_group()\n")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
@@ -194,3 +204,44 @@ def test_bench_sharding_two_ranks_gloo(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     # each rank writes its own file: the two stdout streams interleave under torchrun
     assert (tmp_path / "rank0.txt").read_text() == "[0, 2, 4]" and (tmp_path / "rank1.txt").read_text() == "[1, 3]"
+
+
+def test_grad_buckets_layout():
+    """The data-parallel gradient buffer: bucket k = stage 4 - k (+ its side_prep conv), heads in the last bucket; every
+    gradient-carrying parameter has exactly one view, buckets are contiguous and cover the buffer (59.7 MB for the full VGG:
+    the lr = 0 up-sampling weights are left out)."""
+    from fosvos_b200.sharding import GradBuckets
+    net = FB.OSVOS_VGG(pretrained=0)
+    params = dict(net.named_parameters())
+    bk = GradBuckets(net, params, "cpu")
+    names = net._grad_names()
+    assert sorted(sum(bk.bucket_names, [])) == sorted(names) and not any(n.startswith("upscale") for n in names)
+    assert bk.flat.numel() == sum(params[n].numel() for n in names) == 15267157 - 2 * (16 * 16 + 1) * (16 + 64 + 256 + 1024) // 2
+    assert bk.ranges[0][0] == 0 and bk.ranges[-1][1] == bk.flat.numel()
+    assert all(bk.ranges[i][1] == bk.ranges[i + 1][0] for i in range(4))
+    assert all(n.startswith(("stages.4.", "side_prep.3.")) for n in bk.bucket_names[0])
+    assert [round((hi - lo) * 4 / 1e6, 1) for lo, hi in bk.ranges] == [28.6, 23.9, 6.0, 1.0, 0.2]
+    for n in names:
+        v = bk.view(n)
+        assert v.shape == params[n].shape and v.untyped_storage().data_ptr() == bk.flat.untyped_storage().data_ptr()
+
+
+def test_leaf_modules_are_the_reference_types_and_never_fall_back():
+    """Leaves stay nn.Conv2d / nn.ReLU / nn.MaxPool2d / nn.ConvTranspose2d instances (prune.py:49-50 isinstance checks), plain
+    torch leaves assigned by surgery are adopted, and a leaf called on a CPU tensor raises instead of running a library kernel."""
+    from fosvos_b200 import leaf
+    net = FB.OSVOS_VGG(pretrained=0)
+    assert all(isinstance(m, leaf.Conv2d) for m in net.modules() if isinstance(m, torch.nn.Conv2d))
+    assert isinstance(net.stages[1][0], torch.nn.MaxPool2d) and isinstance(net.stages[0][1], torch.nn.ReLU)
+    net.stages[0][0] = torch.nn.Conv2d(3, 48, 3, padding=1, bias=False)           # prune-style surgery (prune.py:490-514)
+    net.precision = "fp32"
+    assert type(net.stages[0][0]) is leaf.Conv2d and net.stages[0][0]._fosvos_precision == "fp32"
+    for m, x in ((net.stages[0][0], torch.zeros(1, 3, 8, 8)), (net.stages[0][1], torch.zeros(1, 4, 8, 8)), (net.stages[1][0], torch.zeros(1, 4, 8, 8))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(x)
+    with pytest.raises(RuntimeError, match="only fused"):
+        net.upscale[0](torch.zeros(1, 16, 4, 4))
+    h = net.stages[2][3].register_forward_hook(lambda *a: None)
+    assert net._leaf_hooks_present()
+    h.remove()
+    assert not net._leaf_hooks_present()
