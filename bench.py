@@ -337,9 +337,10 @@ def conv_roofline(net, frames, peaks, precision):
                 cp = ops.pad8(conv.out_channels)
                 x = a
                 last = ci == len(convs) - 1
-                if tc and last and si == 0 and net.fuse_pool:
+                poolable = tc and last and si < 4 and cp >= 64 and x.shape[3] > 8 and net.fuse_pool      # (the network's own rule)
+                if poolable and si == 0:
                     plan.append((lambda x=x, pc=pc, cp=cp: ops.conv3x3_pool_only(x, pc.w_fwd, pc.bias, cp, RB), conv, x.shape[1], x.shape[2], "pool-only"))
-                elif tc and last and si < 4 and net.fuse_pool:
+                elif poolable:
                     plan.append((lambda x=x, pc=pc, cp=cp: ops.conv3x3_pool(x, pc.w_fwd, pc.bias, cp, RB), conv, x.shape[1], x.shape[2], "conv+pool"))
                 else:
                     o = torch.empty((x.shape[0], x.shape[1], x.shape[2], cp), dtype=x.dtype, device=x.device)
@@ -474,27 +475,43 @@ def config3_leg(sd0, frames_d, frames_h, peaks, dev, batch=32, reps=3):
 
 
 def side_roofline(net, frames, peaks):
-    """HBM roofline of the fused side-output chain (heads + upsample/fuse/sigmoid/threshold)."""
+    """HBM roofline of the fused side-output chain as the network runs it.  Since round 2 the two 1x1 heads leave the
+    side_prep convolutions' epilogue (conv_side_tc.cu), so in inference the chain is ONE kernel -- transposed-conv
+    up-sampling + crop + fuse + sigmoid + threshold -- that reads 8 B per low-res pixel (the head maps) and writes the five
+    logit maps, the probabilities and the mask: 11.34 MB per 480x854 frame (SURVEY 8d's 14.61 MB counted the 16-channel
+    side_prep maps, 4.36 MB, which are no longer written or read)."""
     from fosvos_b200 import ops
     n = frames.shape[0]
+    fused = net._impl() == "tc" and net.side_tc
     with torch.no_grad():
         _, _, _, saved = net._run_forward(frames, save=True)
         sps, params = saved["sps"], saved["params"]
         mode = 1 if net._side_general else (2 if net._side_separable else 0)      # the path the network itself takes
-        ms = _time_ms(lambda: ops.side_fwd(sps, params, H, W, general=mode, want_prob=True, want_mask=True), reps=10)
-    esz = sps[0].element_size()
-    low = sum(t.shape[1] * t.shape[2] for t in sps)
-    bytes_per_frame = 16 * low * esz + 5 * H * W * 4 + H * W * 4 + H * W       # read sp; write 5 maps + prob + mask
+        hs, ws = [int(t.shape[1]) for t in sps], [int(t.shape[2]) for t in sps]
+        low = sum(h * w for h, w in zip(hs, ws))
+        if fused and mode != 1:
+            zs_flat, zs_views = ops.side_zs_workspace(n, hs, ws, frames.device)
+            heads = ops.side_heads_views(params)
+            for i in range(4):
+                pc = net._packed_for(net.side_prep[i], False)
+                ops.conv3x3_side(saved["stage_out"][i + 1], pc.w_fwd, pc.bias, zs=zs_views[i], heads=heads[i], want_y=False)
+            ms = _time_ms(lambda: ops.side_fwd_heads_done(zs_flat, hs, ws, params, n, H, W, general=mode, want_prob=True, want_mask=True), reps=10)
+            bytes_per_frame = 8 * low + 5 * H * W * 4 + H * W * 4 + H * W            # read head maps; write 5 maps + prob + mask
+            kernel = "side_upsample_sep2_kernel" if mode == 2 and W % 2 == 0 else "side_upsample_sep_kernel" if mode == 2 else "side_upsample_kernel"
+        else:
+            ms = _time_ms(lambda: ops.side_fwd(sps, params, H, W, general=mode, want_prob=True, want_mask=True), reps=10)
+            bytes_per_frame = 16 * low * sps[0].element_size() + 5 * H * W * 4 + H * W * 4 + H * W       # read sp; write 5 maps + prob + mask
+            kernel = "side_heads2_kernel + side_upsample kernel"
     achieved = bytes_per_frame * n / (ms / 1e3) / 1e9
-    # DRAM bytes of the two launches from the committed ncu --set full capture (only if it was taken at this batch)
+    # DRAM bytes of the launch from the committed ncu --set full capture (only if it was taken at this batch)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01i_side_traffic.json")
-    if mode == 2 and W % 2 == 0 and esz == 2 and os.path.exists(tp):
+    tp = os.path.join(ROOT, "profiles", "r02_side_traffic.json")
+    if fused and os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("batch") == n:
             traffic = tj["traffic_bytes"]
-    return dict(bound="hbm", kernel="side_heads2_kernel + " + ("side_upsample_sep2_kernel" if mode == 2 and W % 2 == 0 else "side_upsample_sep_kernel" if mode == 2 else "side_upsample_kernel"), achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
-                frac=achieved / peaks["hbm_gbs"], traffic=traffic, batch=n, ms=ms, bytes_per_frame=bytes_per_frame)
+    return dict(bound="hbm", kernel=kernel, achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=traffic,
+                batch=n, ms=ms, bytes_per_frame=bytes_per_frame, survey_bytes_per_frame=16 * low * 2 + 5 * H * W * 4 + H * W * 4 + H * W)
 
 
 def loss_roofline(n, dev, peaks):

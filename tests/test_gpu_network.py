@@ -468,7 +468,10 @@ def test_forward_hooks_fire_with_the_kernel_outputs():
     outs = net(x.to(DEV))
     assert "out" in seen and seen["out"].shape == inter["stages.2.3"].shape
     # the oracle's intermediate is post-ReLU (F.relu(F.conv2d(...))); the hooked conv output is pre-ReLU
-    assert torch.allclose(torch.relu(seen["out"]).cpu(), inter["stages.2.3"].detach(), rtol=1e-4, atol=1e-4)
+    act = inter["stages.2.3"].detach()
+    # (cancelling fp32 sums over K = 2304 terms: the bound is relative to the map's scale)
+    assert torch.allclose(torch.relu(seen["out"]).detach().cpu(), act, rtol=1e-4, atol=2e-4 * float(act.abs().max())), \
+        float((torch.relu(seen["out"]).detach().cpu() - act).abs().max())
     for o, r in zip(outs, fix["outs"]):
         assert float((torch.sigmoid(o.detach().cpu()) - torch.sigmoid(r)).abs().max()) <= 1e-4
     FB.class_balanced_cross_entropy_loss(outs[-1], m.to(DEV), size_average=False).backward()
@@ -490,7 +493,7 @@ def test_forward_hooks_fire_with_the_kernel_outputs():
     # a leaf called on its own runs the repo's conv kernel (not cuDNN): compare with the oracle's arithmetic
     y = net.stages[0][0](x.to(DEV))
     ref = torch.nn.functional.conv2d(x, sd["stages.0.0.weight"], sd["stages.0.0.bias"], padding=1)
-    assert torch.allclose(y.detach().cpu(), ref, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(y.detach().cpu(), ref, rtol=1e-4, atol=2e-4 * float(ref.abs().max())), float((y.detach().cpu() - ref).abs().max())
     with pytest.raises(RuntimeError, match="only fused"):
         net.fuse(torch.zeros(1, 64, 8, 8, device=DEV))
     with pytest.raises(RuntimeError, match="only fused"):

@@ -48,7 +48,15 @@ for batch in [int(a) for a in sys.argv[1:]] or [1, 5, 16]:
         h, w = (h + 1) // 2, (w + 1) // 2
         sps.append(torch.randn((batch, h, w, 16), device=dev).to(torch.bfloat16))
     low = sum(t.shape[1] * t.shape[2] for t in sps)
-    t = timeit(lambda: ops.side_fwd(sps, params, H, W, general=2, want_prob=True, want_mask=True))
-    b = (16 * low * 2 + 5 * H * W * 4 + H * W * 4 + H * W) * batch
+    if os.environ.get("FOSVOS_SIDE_PROBE_HEADS", "done") == "done":
+        # the path the network takes since round 2: the side_prep convolutions wrote the head maps (conv_side_tc.cu), the side
+        # chain is the up-sampling kernel alone -- reads 8 B per low-res pixel, writes 5 maps + prob + mask
+        hs, ws = [int(t_.shape[1]) for t_ in sps], [int(t_.shape[2]) for t_ in sps]
+        zs = torch.randn((batch * low, 2), device=dev)
+        t = timeit(lambda: ops.side_fwd_heads_done(zs, hs, ws, params, batch, H, W, general=2, want_prob=True, want_mask=True))
+        b = (8 * low + 5 * H * W * 4 + H * W * 4 + H * W) * batch
+    else:
+        t = timeit(lambda: ops.side_fwd(sps, params, H, W, general=2, want_prob=True, want_mask=True))
+        b = (16 * low * 2 + 5 * H * W * 4 + H * W * 4 + H * W) * batch
     out.append(f"b{batch}: {t:.1f} us {b / t / 1e3:.0f} GB/s")
 print(" | ".join(out))
