@@ -500,10 +500,12 @@ def test_forward_hooks_fire_with_the_kernel_outputs():
         net.upscale[0](torch.zeros(1, 16, 8, 8, device=DEV))
     # bf16: the hooked path goes through the tcgen05 kernels
     net.precision = "bf16"
-    h = net.stages[2][3].register_forward_hook(hook)
+    seen16 = {}
+    h = net.stages[2][3].register_forward_hook(lambda mod, inp, out: seen16.__setitem__("out", out))
     with torch.no_grad():
         outs3 = net(x.to(DEV))
     h.remove()
+    assert seen16["out"].shape == act.shape
     tol = _tol("bf16", "random", sd, x, fix["outs"])
     assert float((torch.sigmoid(outs3[4].cpu()) - torch.sigmoid(fix["outs"][4])).abs().max()) <= tol
 
