@@ -55,7 +55,13 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_BIAS_BYTES = 2048;  // all CoutP <= 512 biases, staged once per CTA
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one 64-channel output slab of a tile
-constexpr int MODE_GENERIC = 0, MODE_C8 = 1, MODE_HALO = 2;
+constexpr int MODE_GENERIC = 0, MODE_C8 = 1, MODE_HALO = 2, MODE_K16 = 3;
+// MODE_K16: MODE_HALO for Cin == 16 (the data gradient of side_prep: dA = conv(dsp (16 ch), W^T)).  The generic path pads the
+// 16 channels to a 64-channel K slab, i.e. issues four K = 16 MMAs per tap of which three multiply zeros; here a tap is ONE
+// MMA: activation boxes {16 ch, TW, TH + 2} and weight boxes {16, BN} land as 32-byte rows in the SWIZZLE_32B K-major layout
+// (8-row atoms of 256 B; a vertical tap is r * TW rows = a multiple of the atom further).
+__host__ __device__ constexpr bool tc_halo_like(int mode) { return mode == MODE_HALO || mode == MODE_K16; }
+__host__ __device__ constexpr int tc_row_bytes(int mode) { return mode == MODE_K16 ? 32 : 128; }   // bytes of one pixel / weight row in a K slab
 constexpr int TC_FLAG_SKIP_B = 1 << 21;          // internal (FOSVOS_TC_SKIP_B=1): timing experiment, weight tiles are not loaded
 constexpr int TC_FLAG_SKIP_A = 1 << 22;          // internal (FOSVOS_TC_SKIP_A=1): timing experiment, activation boxes are not loaded
 constexpr int TC_FLAG_MASK_IN_REGS = 1 << 20;    // internal (FOSVOS_TC_MASK_REGS=1): apply the ReLU mask in the register phase
@@ -67,25 +73,29 @@ constexpr int C8_KBLOCKS = 10;                   // 9 taps + 1 zero-weight pad -
 constexpr int C8_W_BYTES = C8_KBLOCKS * 64 * 16; // [k block][64 couts][8 ch]
 
 template <int BN, int MODE> struct TcCfg {
-  static constexpr int A_BYTES = MODE == MODE_C8 ? C8_A_BYTES : MODE == MODE_HALO ? HALO_A_BYTES : TC_A_BYTES;
-  static constexpr int B_BYTES = MODE == MODE_C8 ? 0 : BN * TC_BK * 2;
+  static constexpr int A_BYTES = MODE == MODE_C8 ? C8_A_BYTES : MODE == MODE_HALO ? HALO_A_BYTES : MODE == MODE_K16 ? HALO_A_BYTES / 4 : TC_A_BYTES;
+  static constexpr int B_BYTES = MODE == MODE_C8 ? 0 : BN * tc_row_bytes(MODE);
   // MODE_HALO: two rings -- STAGES halo boxes (A) followed by B_STAGES weight tiles (B); otherwise one ring of A+B
   // generic narrow tiles (side_prep, N = 16/32): two 64-channel K blocks per stage -- the MMAs are issue-bound (~57 cycles
   // each), a barrier round trip per four of them is a measurable tax
   static constexpr int K_GROUP = (MODE == MODE_GENERIC && BN <= 32) ? 2 : 1;
-  static constexpr int STAGE_BYTES = MODE == MODE_HALO ? A_BYTES : K_GROUP * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 3 : (BN >= 128) ? 4 : (BN >= 64) ? 4 : 6)
+  static constexpr int STAGE_BYTES = tc_halo_like(MODE) ? A_BYTES : K_GROUP * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = MODE == MODE_K16 ? 6 : MODE == MODE_HALO ? ((BN >= 256) ? 3 : (BN >= 128) ? 4 : (BN >= 64) ? 4 : 6)
                                 : MODE == MODE_C8 ? 8 : (BN >= 256) ? 3 : (BN >= 128) ? 5 : (BN >= 64) ? 7 : 5;
   // narrow tiles: one B stage = the three vertical taps of a kernel column (a N = 64 MMA is issue-bound at ~57 cycles, so
   // a barrier round trip per four MMAs costs a third on top; twelve MMAs per wait bring it under 10 %)
-  static constexpr int B_GROUP = (MODE == MODE_HALO && BN <= 64) ? 3 : 1;
+  static constexpr int B_GROUP = (MODE == MODE_K16 || (MODE == MODE_HALO && BN <= 64)) ? 3 : 1;
   static constexpr int B_STAGE_BYTES = B_GROUP * B_BYTES;
-  static constexpr int B_STAGES = MODE == MODE_HALO ? ((BN >= 256) ? 4 : (BN >= 128) ? 6 : 4) : 0;
+  static constexpr int B_STAGES = MODE == MODE_K16 ? 6 : MODE == MODE_HALO ? ((BN >= 256) ? 4 : (BN >= 128) ? 6 : 4) : 0;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES + B_STAGES * B_STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   // BN >= 64: each epilogue group stages 64-channel output slabs (128 px x 128 B, SWIZZLE_128B) for TMA stores
   static constexpr bool STAGED = BN >= 64;
-  static constexpr int STAGING_BYTES = STAGED ? 2 * TC_SLAB_BYTES : 0;
+  // slabs in flight per epilogue group.  The first layer is bound by its 52 MB/frame output write: with one 16 KB slab per
+  // group a CTA keeps 32 KB of stores in flight (4.7 MB chip-wide), too little to cover the store latency at HBM rate
+  // (Little: ~7 TB/s x ~1.5 us = 11 MB); its tiny operand ring leaves room for four slabs per group.
+  static constexpr int STAGING_BUFS = MODE == MODE_C8 ? 4 : 1;
+  static constexpr int STAGING_BYTES = STAGED ? 2 * STAGING_BUFS * TC_SLAB_BYTES : 0;
   static constexpr int WRES_BYTES = MODE == MODE_C8 ? C8_W_BYTES : 0;
   static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + WRES_BYTES + TC_BIAS_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -220,7 +230,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         __syncwarp();
         a_dst += Cfg::STAGE_BYTES; bar_full += 8; bar_empty += 8;
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; a_dst = tiles_a; bar_full = full_a; bar_empty = empty_a; }
-      } else if constexpr (MODE == MODE_HALO) {
+      } else if constexpr (tc_halo_like(MODE)) {
         for (int c = 0; c < p.cin_pad; c += TC_BK) {
           for (int s = 0; s < 3; ++s) {
             ptx::mbar_wait_a(bar_empty, phase ^ 1);
@@ -290,14 +300,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint32_t phase = 0;
     int it = 0;
     // SWIZZLE_128B K-major descriptor: low word = start address >> 4 | LBO(1) << 16, high word constant
-    const uint64_t desc0 = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(tiles));
+    const uint64_t desc0 = MODE == MODE_K16 ? ptx::umma_desc_sw32_kmajor(ptx::smem_u32(tiles)) : ptx::umma_desc_sw128_kmajor(ptx::smem_u32(tiles));
     const uint32_t a_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
     const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
     uint32_t a_lo = a_lo0, bar_full = full_a, bar_empty = empty_a;
     // weight-tile ring (MODE_HALO)
     int bstage = 0;
     uint32_t bphase = 0;
-    const uint32_t b_lo0 = (uint32_t)ptx::umma_desc_sw128_kmajor(ptx::smem_u32(btiles));
+    const uint32_t b_lo0 = (uint32_t)(MODE == MODE_K16 ? ptx::umma_desc_sw32_kmajor(ptx::smem_u32(btiles)) : ptx::umma_desc_sw128_kmajor(ptx::smem_u32(btiles)));
     const uint32_t bfull_a = ptx::smem_u32(bfull_bar), bempty_a = ptx::smem_u32(bempty_bar);
     uint32_t b_lo = b_lo0, bbar_full = bfull_a, bbar_empty = bempty_a;
     (void)bstage; (void)bphase; (void)b_lo; (void)bbar_full; (void)bbar_empty;
@@ -328,9 +338,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         __syncwarp();
         bar_full += 8; bar_empty += 8;
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; bar_full = full_a; bar_empty = empty_a; }
-      } else if constexpr (MODE == MODE_HALO) {
+      } else if constexpr (tc_halo_like(MODE)) {
         const uint32_t tfull = ptx::smem_u32(&tmem_full[as]);
-        const uint32_t tap_step = (uint32_t)(TW * 128) >> 4;      // one image row of the patch, in descriptor units
+        const uint32_t tap_step = (uint32_t)(TW * tc_row_bytes(MODE)) >> 4;      // one image row of the patch, in descriptor units
+        constexpr int K_STEPS = MODE == MODE_K16 ? 1 : TC_BK / 16;                // K = 16 MMAs per slab
         const int n_boxes = 3 * p.k_chunks;
         uint32_t acc = 0;
         for (int bx = 0; bx < n_boxes; ++bx) {
@@ -342,7 +353,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
               for (int g = 0; g < Cfg::B_GROUP; ++g) {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
+                for (int k = 0; k < K_STEPS; ++k) {
                   ptx::umma_bf16_lohi(tmem_d, a_lo + (r + g) * tap_step + 2 * k, b_lo + g * (Cfg::B_BYTES >> 4) + 2 * k, desc_hi, idesc,
                                       acc | g | k);
                 }
@@ -404,8 +415,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const bool issuer = ((e & 7) == 0) && (lane == 0);    // owns this group's TMA-store bulk groups
     const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
     constexpr int GRP_THREADS = 32 * TC_EPI_WARPS / 2;
-    uint8_t* buf = staging + grp * TC_SLAB_BYTES;
-    const uint32_t buf_a = ptx::smem_u32(buf);
+    uint8_t* const buf0 = staging + grp * Cfg::STAGING_BUFS * TC_SLAB_BYTES;
+    int cur_buf = 0;                                       // staging slab of the next store (group-uniform)
     const int as = grp;
     const bool relu = (p.flags & FOSVOS_CONV_RELU) != 0;
     const uint32_t bias_a = ptx::smem_u32(bias_s);
@@ -532,7 +543,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
           }
           if (live && p.y) {                              // (y == nullptr: pool-only launch, nothing but the pooled map leaves)
-            if (issuer) ptx::tma_store_wait_read<0>();    // the previous store of this group has read the buffer
+            uint8_t* const buf = buf0 + cur_buf * TC_SLAB_BYTES;
+            const uint32_t buf_a = ptx::smem_u32(buf);
+            if (Cfg::STAGING_BUFS > 1) cur_buf = cur_buf + 1 == Cfg::STAGING_BUFS ? 0 : cur_buf + 1;
+            // the store that last used this slab has read it (the STAGING_BUFS - 1 younger ones may still be in flight)
+            if (issuer) ptx::tma_store_wait_read<Cfg::STAGING_BUFS - 1>();
             ptx::named_bar_sync(bar_a, GRP_THREADS);
             const uint32_t rowp = buf_a + row * 128;
 #pragma unroll
@@ -634,7 +649,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // (C, W, H, N) view of an NHWC tensor; box = {box_c channels, TW, TH, 1}
-static int encode_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int C, int TW, int TH, int box_c, bool swizzle) {
+static int encode_act_map(CUtensorMap* m, const void* x, int N, int H, int W, int C, int TW, int TH, int box_c, bool swizzle, bool sw32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -642,7 +657,7 @@ static int encode_act_map(CUtensorMap* m, const void* x, int N, int H, int W, in
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations %dx%dx%dx%d box %dx%dx%d) failed: %d", N, H, W, C, TH, TW, box_c, (int)r); return FOSVOS_ERR_DRIVER; }
   return FOSVOS_OK;
@@ -663,15 +678,15 @@ static int encode_c8_map(CUtensorMap* m, const void* x, int N, int H, int W) {
   return FOSVOS_OK;
 }
 
-static int encode_w_map(CUtensorMap* m, const void* w, int rows, int kdim, int BN) {
+static int encode_w_map(CUtensorMap* m, const void* w, int rows, int kdim, int BN, bool k16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
   cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+  cuuint32_t box[2] = {(cuuint32_t)(k16 ? 16 : TC_BK), (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, k16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%d box %d) failed: %d", rows, kdim, BN, (int)r); return FOSVOS_ERR_DRIVER; }
   return FOSVOS_OK;
@@ -739,9 +754,11 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   const bool c8 = taps == 9 && Cin == 8 && Cout <= 64 && !getenv("FOSVOS_TC_NO_C8");
   // narrow outputs (side_prep, N = 16) are bound by the MMA issue rate, not by L2 traffic: they keep one ring
   const bool halo = taps == 9 && !c8 && Cout > 32 && !getenv("FOSVOS_TC_NO_HALO");
+  // 16 input channels (the side_prep data gradient): one K = 16 MMA per tap instead of a zero-padded 64-channel slab
+  const bool k16 = halo && Cin == 16 && !getenv("FOSVOS_TC_NO_K16");
   p.tw_shift = c8 ? 3 : halo ? pick_tw_shift(H, W, 3, 4) : pick_tw_shift(H, W, 2, 6);
   const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
-  p.halo_bytes = (TH + 2) * TW * 128;
+  p.halo_bytes = (TH + 2) * TW * (k16 ? 32 : 128);
   p.tiles_x = ceil_div(W, TW);
   p.tiles_y = ceil_div(H, TH);
   p.k_chunks = ceil_div(Cin, TC_BK);
@@ -786,6 +803,7 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
 
   CUtensorMap mx, mw, my;
   int rc = c8     ? encode_c8_map(&mx, x, N, H, W)
+           : k16  ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH + 2, 16, true, true)
            : halo ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH + 2, TC_BK, true)
                   : encode_act_map(&mx, x, N, H, W, Cin, TW, TH, TC_BK, true);
   if (rc) return rc;
@@ -793,10 +811,17 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   // just has to encode, so it describes the input tensor
   rc = y ? encode_act_map(&my, y, N, H, W, Cout, TW, TH, TC_BK, true) : encode_act_map(&my, x, N, H, W, Cin, TW, TH, TC_BK, true);
   if (rc) return rc;
-  rc = encode_w_map(&mw, w_packed, Cout, taps * p.cin_pad, BN);
+  rc = encode_w_map(&mw, w_packed, Cout, taps * p.cin_pad, BN, k16);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (c8) return launch_tc<64, MODE_C8>(mx, mw, my, p, st);
+  if (k16) {
+    switch (BN) {
+      case 64: return launch_tc<64, MODE_K16>(mx, mw, my, p, st);
+      case 128: return launch_tc<128, MODE_K16>(mx, mw, my, p, st);
+      default: return launch_tc<256, MODE_K16>(mx, mw, my, p, st);
+    }
+  }
   if (halo) {
     switch (BN) {
       case 16: return launch_tc<16, MODE_HALO>(mx, mw, my, p, st);

@@ -252,6 +252,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same for SWIZZLE_32B: rows of 32 B (16 bf16 = one K step), 8-row atoms 256 B apart.  [61,64) layout = 6
+__device__ __forceinline__ uint64_t umma_desc_sw32_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, M x N tile.
 //   [4,6) D fmt = 1 (F32)  [7,10) A fmt = 1 (BF16)  [10,13) B fmt = 1  [15] A major = 0  [16] B major = 0
 //   [17,23) N >> 3         [24,29) M >> 4

@@ -75,6 +75,11 @@ CONV_CASES = [
     (1, 12, 20, 64, 16),
     (1, 10, 18, 192, 32),
     (2, 14, 9, 32, 32),
+    # 16 input channels and a wide output: MODE_K16 (one K = 16 MMA per tap, SWIZZLE_32B operands) on the tensor-core path
+    (1, 17, 23, 16, 128),
+    (2, 9, 40, 16, 256),
+    (1, 30, 54, 16, 512),
+    (1, 12, 11, 16, 40),
 ]
 
 
@@ -223,11 +228,13 @@ def test_side_fwd_from_fused_heads_matches_heads_kernel():
         assert torch.allclose(b, c, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("shape", [(1, 13, 18, 64, 128), (2, 13, 18, 128, 16), (1, 30, 54, 512, 16), (1, 9, 35, 40, 16)])
 @pytest.mark.parametrize("impl,dt", [("simt", torch.float32), ("tc", torch.bfloat16)])
-def test_conv3x3_mask_accumulate_dgrad(impl, dt):
-    """The data-gradient use of the kernel: flipped/transposed weights, ReLU mask, += fan-in."""
+def test_conv3x3_mask_accumulate_dgrad(impl, dt, shape):
+    """The data-gradient use of the kernel: flipped/transposed weights, ReLU mask, += fan-in.  cout = 16 is the
+    side_prep data gradient: on the tensor-core path one K = 16 MMA per tap (conv_tc.cu MODE_K16, SWIZZLE_32B operands)."""
     g = _gen(5)
-    n, h, w_, cin, cout = 1, 13, 18, 64, 128
+    n, h, w_, cin, cout = shape
     x = torch.randn(n, cin, h, w_, generator=g).clamp_min(0)             # post-ReLU activation (has zeros)
     wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
     dz = torch.randn(n, cout, h, w_, generator=g)
