@@ -777,6 +777,10 @@ def config5_leg(args, rank, world, dev, sd0, frames_d, masks_d, windows=6):
         e0.record(); tr.run(windows * n_local); e1.record(); torch.cuda.synchronize(); sharding.barrier()
         ms = sharding.max_over_ranks(e0.elapsed_time(e1)) / windows
         res[name] = dict(ms_per_optimizer_step=ms, micro_iterations_per_s=world * n_local / (ms / 1e3))
+        if overlap:
+            res[name]["window_captured_in_cuda_graph"] = tr._overlap_graph is not None
+            if tr.overlap_capture_error:
+                res[name]["capture_error"] = tr.overlap_capture_error
         del tr, net
         torch.cuda.empty_cache()
     base = res["no_exchange"]["ms_per_optimizer_step"]

@@ -15,6 +15,7 @@ frame size and reused for every sequence the process handles.
 from __future__ import annotations
 
 import functools
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -210,7 +211,8 @@ class OnlineTrainer:
         self._calls_micro = 0
         self._calls_window = 0
         self._comm_stream: Optional[torch.cuda.Stream] = None
-        self.exposed_allreduce_ms: Optional[float] = None
+        self._overlap_graph = None
+        self.overlap_capture_error: Optional[str] = None
 
     # shared between the trainers of one network (see ``share_with``)
     @property
@@ -485,7 +487,11 @@ class OnlineTrainer:
                 if self.overlap_ar:
                     if self.use_graph and self._step_graph is None:
                         self._capture_overlap_warmup()
-                    self._window_overlapped()
+                    if self._overlap_graph is not None:
+                        self._overlap_graph.replay()            # the window with its NCCL calls inside, one graph launch
+                        L.CALLS[0] += self._calls_window
+                    else:
+                        self._window_overlapped()
                     if losses_out is not None:
                         losses_out.extend(float(v) for v in self.window_losses.tolist())
                     done += self.n
@@ -539,6 +545,33 @@ def _capture_overlap_warmup(self: OnlineTrainer) -> None:
     self.optimizer._ensure_table()
     _repack_in_place(self.net)
     self._capture_step(None)
+    # One eager overlapped window (builds the bucket fold tables, warms the NCCL channels), cleared again; then the same
+    # window -- forks to the auxiliary and the communication stream, per-bucket folds and NCCL all-reduces included -- is
+    # captured into ONE graph, so the exchange overlaps the backward pass without ~100 eager launches per window.
+    self._overlap_graph = None
+    if os.environ.get("FOSVOS_DP_GRAPH", "1") != "0":
+        saved_sum = self.loss_sum.clone()
+        self._window_overlapped()
+        torch.cuda.current_stream(self.device).synchronize()
+        for g in self.grads.values():
+            g.zero_()
+        for ws in (self.wgrad_ws or {}).values():
+            ws.zero_()
+        self.loss_sum.copy_(saved_sum)
+        try:
+            c0 = L.CALLS[0]
+            graph = torch.cuda.CUDAGraph()
+            hp = torch.cuda.Stream(device=self.device, priority=-1)
+            hp.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.graph(graph, stream=hp, pool=self._step_graph.pool()):
+                self._window_overlapped()
+            torch.cuda.current_stream(self.device).wait_stream(hp)
+            self._overlap_graph, self._calls_window = graph, L.CALLS[0] - c0
+        except Exception as ex:                      # a PyTorch / NCCL build that cannot capture collectives: stay eager
+            self._overlap_graph = None
+            self.overlap_capture_error = f"{type(ex).__name__}: {ex}"[:300]
+            torch.cuda.synchronize(self.device)
+    _sync_cache_keys(self.net)
 
 
 OnlineTrainer._capture_overlap_warmup = _capture_overlap_warmup
