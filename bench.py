@@ -258,6 +258,11 @@ def run_ours(args):
             extras["roofline_wgrad"], extras["roofline_dgrad"] = backward_rooflines(new_net(), frames_d, peaks, args.avg_grad_every_n)
             if args.config3:
                 extras["config3"] = config3_leg(sd0, frames_d, frames_h, peaks, dev)
+            if args.fp32_modes:
+                try:
+                    extras["fp32_modes"] = fp32_modes_leg(sd0, frames_d, frames_h, dev)
+                except Exception as ex:
+                    extras["fp32_modes"] = {"error": f"{type(ex).__name__}: {ex}"[:400]}
         ft_tflops = ITER_GFLOP * args.iters * args.steps / (t_ft_max / 1e3) / 1e3 if t_ft_max > 0 else None
         if ft_tflops:
             extras["roofline_step"] = dict(bound="tensor", kernel="one fine-tune step: fused 5-iteration window (forward, loss, backward) + optimizer step, as timed in `value`",
@@ -720,6 +725,40 @@ def parity_check(net, trainer, sd0, frames_d, masks_d, frames_h, args, losses_ou
     return res
 
 
+def fp32_modes_leg(sd0, frames_d, frames_h, dev, batch=8):
+    """The strict-parity modes next to each other (inference, batch 8 at 480x854): 'fp32' = direct fp32-FMA kernels,
+    'fp32_tc' = fp32-equivalent arithmetic on the tcgen05 kernels (three bf16 terms per operand, six products, fp32
+    accumulation), 'bf16x3' = two terms / three products; each with its max|dprob| against the CPU fp32 oracle on frame 0."""
+    import fosvos_b200 as FB
+    from oracle import osvos_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = O.vgg_forward(sd0, frames_h[0:1])
+    out = {}
+    for prec in ("fp32", "fp32_tc", "bf16x3", "bf16"):
+        net = FB.OSVOS_VGG(pretrained=0)
+        net.load_state_dict(sd0)
+        net = net.to(dev)
+        net.precision = prec
+        fb = frames_d[:batch]
+        with torch.no_grad():
+            outs, _, _ = net.predict(fb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 2 if prec == "fp32" else 4
+            e0.record()
+            for _ in range(reps):
+                net.predict(fb)
+            e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        err = max(float((torch.sigmoid(o[0:1].cpu()) - torch.sigmoid(r)).abs().max()) for o, r in zip(outs, ref))
+        out[prec] = dict(frames_per_s=batch / (ms / 1e3), ms_per_batch=ms, max_dprob_vs_cpu_fp32_oracle=err)
+        del net
+        torch.cuda.empty_cache()
+    out["workload"] = f"net.predict on {batch} x 480x854 frames (ingest -> 5 maps + prob + mask), parent weights"
+    return out
+
+
 def config4_leg(args, rank, world, dev, sd_dev, trainer, net, n_sequences=20):
     """BASELINE configs[3]: the DAVIS-2016-val-shaped pipeline -- 20 synthetic sequences x `args.frames` frames, per-sequence
     fine-tune + inference, sequence i on rank i % world (train_online.py:184-186), no collective.  Every rank works through
@@ -869,6 +908,7 @@ def main():
                     help="run the avg_grad_every_n micro-iterations between two optimizer steps as one batched pass (same gradients)")
     ap.add_argument("--weights", default="parent", choices=["parent", "structured"],
                     help="synthetic parent network (synth.make_state_dict kind); 'structured' is the round-1 set on which the lr=1e-8 fine-tune diverges")
+    ap.add_argument("--fp32-modes", type=int, default=1, help="N=1: inference throughput / error of the strict modes (fp32 direct, fp32_tc, bf16x3)")
     ap.add_argument("--config3", type=int, default=1, help="N=1: BASELINE configs[2] line (pruned 50 %, batch 32, bf16)")
     ap.add_argument("--config4", type=int, default=1, help="BASELINE configs[3] leg: 20 sequences sharded by sequence over the ranks")
     ap.add_argument("--config5", type=int, default=1, help="N>1: BASELINE configs[4] leg: data-parallel offline step with the gradient all-reduce")

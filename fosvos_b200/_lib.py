@@ -36,6 +36,13 @@ SIGNATURES = {
     "fosvos_conv3x3_tc_pool": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_side_tc_supported": (_i, [_i]),
     "fosvos_conv3x3_side_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fosvos_split_pairs": (_i, [_i]),
+    "fosvos_split_weight_term": (_i, [_i, _i]),
+    "fosvos_split_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_packed_weight_split_elems": (_ll, [_i, _i, _i]),
+    "fosvos_pack_conv3x3_weight_split": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_conv3x3_tc_split": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_maxpool2x2_split": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_simt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_wgrad_tc_workspace_bytes": (C.c_size_t, [_i, _i]),
     "fosvos_conv3x3_wgrad_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

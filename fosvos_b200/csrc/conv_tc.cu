@@ -116,7 +116,27 @@ struct TcParams {
   uint32_t dn_mul, dn_shift, dx_mul, dx_shift, dy_mul, dy_shift;   // fast division by n_tiles_n, tiles_x, tiles_y
   int halo_bytes;                // MODE_HALO: (TH+2) * TW * 128
   int flags;
+  // split-operand mode (fp32 through the bf16 tensor cores, `fosvos_conv3x3_tc_split`): the activation tensor holds the
+  // bf16 terms of an fp32 map side by side, [x1 | x2 | x3] with seg_len channels each; the GEMM-K walk covers one seg_len
+  // segment per kept product x_i * w_j, and segment g reads activation term (seg_map >> 4 g) & 15
+  int seg_len;                   // 0 = off
+  uint32_t seg_map;
+  int split_planes;              // output terms written by the slab epilogue (1 = plain bf16 output)
+  int plane_stride;              // channels between two output terms (a multiple of 64)
+  float* y_f32;                  // narrow epilogue (BN <= 32): fp32 output instead of bf16 (or null)
 };
+
+// activation channel of GEMM-K position c (a multiple of 64) in split-operand mode
+__device__ __forceinline__ int tc_act_chan(const TcParams& p, int c) {
+  if (p.seg_len == 0) return c;
+  const int g = c / p.seg_len;
+  return (int)((p.seg_map >> (4 * g)) & 15u) * p.seg_len + (c - g * p.seg_len);
+}
+// term t (0, 1, 2) of the bf16 expansion of v: x1 = bf16(v), x2 = bf16(v - x1), x3 = bf16(v - x1 - x2)
+__device__ __forceinline__ float tc_split_term(float v, int t) {
+  for (int i = 0; i < t; ++i) v -= __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
 
 // Un-swizzled K-major operand: 8-row x 16-byte core matrices; `lbo` = byte distance between the two K core
 // matrices of one K=16 step, `sbo` = byte distance between consecutive 8-row groups.
@@ -129,7 +149,10 @@ __device__ __forceinline__ uint64_t umma_desc_noswizzle_kmajor(uint32_t smem_add
   return d;
 }
 
-template <int BN, int MODE>
+// SPLIT: the split-operand instantiation (fp32 through the bf16 tensor cores): remapped activation channels in the
+// producers, bf16-term planes or fp32 out of the epilogue.  A separate instantiation so that the plain bf16 kernels keep
+// their register allocation.
+template <int BN, int MODE, bool SPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_y, const TcParams p) {
@@ -239,7 +262,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 ptx::mbar_expect_tx_a(bar_full, 0);
               } else {
                 ptx::mbar_expect_tx_a(bar_full, p.halo_bytes);
-                ptx::tma_load_4d_a(a_dst, &map_x, bar_full, c, x0 + s - 1, y0 - 1, n);
+                ptx::tma_load_4d_a(a_dst, &map_x, bar_full, SPLIT ? tc_act_chan(p, c) : c, x0 + s - 1, y0 - 1, n);
               }
             }
             __syncwarp();
@@ -279,7 +302,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
                 for (int g = 0; g < Cfg::K_GROUP; ++g) {
                   if (g < ng) {
-                    ptx::tma_load_4d_a(a_dst + g * (Cfg::A_BYTES + Cfg::B_BYTES), &map_x, bar_full, c + g * TC_BK, xx, yy, n);
+                    ptx::tma_load_4d_a(a_dst + g * (Cfg::A_BYTES + Cfg::B_BYTES), &map_x, bar_full, SPLIT ? tc_act_chan(p, c + g * TC_BK) : c + g * TC_BK, xx, yy, n);
                     ptx::tma_load_2d_a(a_dst + g * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::A_BYTES, &map_w, bar_full, wk + g * TC_BK, n0);
                   }
                 }
@@ -464,8 +487,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         // 64-channel slabs: TMEM -> registers -> bias/ReLU/mask/accumulate -> bf16 -> swizzled smem -> one TMA store
         // (the store clips the patch at the frame edge and the channel tail)
         constexpr int SLABS = BN / 64;
+        const int n_planes = SPLIT ? p.split_planes : 1;  // the bf16 terms of the fp32 result, written side by side
 #pragma unroll 1
-        for (int j = 0; j < SLABS; ++j) {
+        for (int jp = 0; jp < SLABS * n_planes; ++jp) {
+          const int j = jp / n_planes, plane = jp - j * n_planes;
           const int co0 = n0 + 64 * j;
           const bool live = co0 < p.CoutP;                // uniform: N-tail tiles have dead slabs
           uint32_t packed[16];
@@ -482,7 +507,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               v[2] = __uint_as_float(r[8 * h + 2]) + __uint_as_float(b0.z); v[3] = __uint_as_float(r[8 * h + 3]) + __uint_as_float(b0.w);
               v[4] = __uint_as_float(r[8 * h + 4]) + __uint_as_float(b1.x); v[5] = __uint_as_float(r[8 * h + 5]) + __uint_as_float(b1.y);
               v[6] = __uint_as_float(r[8 * h + 6]) + __uint_as_float(b1.z); v[7] = __uint_as_float(r[8 * h + 7]) + __uint_as_float(b1.w);
-              if (post) {
+              if (SPLIT) {
+                // split output: term `plane` of the (ReLU'd) fp32 value; the accumulator is re-read per term instead of
+                // keeping 32 more registers live
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = tc_split_term(relu ? fmaxf(v[q], 0.f) : v[q], plane);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) packed[4 * h + q] = ptx::cvt_bf16x2(v[2 * q], v[2 * q + 1]);
+              } else if (post) {
                 if (relu) {
 #pragma unroll
                   for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
@@ -537,7 +569,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               }
             }
           }
-          if (j == SLABS - 1) {                           // all TMEM reads of this tile are done: hand the accumulator back
+          if (jp == SLABS * n_planes - 1) {               // all TMEM reads of this tile are done: hand the accumulator back
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
@@ -565,12 +597,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 v.x &= __vcmpne2(mk[jj].x, 0u); v.y &= __vcmpne2(mk[jj].y, 0u); v.z &= __vcmpne2(mk[jj].z, 0u); v.w &= __vcmpne2(mk[jj].w, 0u);
                 ptx::sts128(sp, v);
               }
-              if (j + 1 < SLABS) load_mask(n0 + 64 * (j + 1));      // in flight during the next slab's TMEM load and math
+              if (j + 1 < SLABS) load_mask(n0 + 64 * (j + 1));      // in flight during the next slab's TMEM load and math (never with split output)
             }
             ptx::fence_proxy_async_smem();
             ptx::named_bar_sync(bar_b, GRP_THREADS);
             if (issuer) {
-              ptx::tma_store_4d(&map_y, buf, co0, x0, y0, n);
+              ptx::tma_store_4d(&map_y, buf, SPLIT ? co0 + plane * p.plane_stride : co0, x0, y0, n);
               ptx::tma_store_commit();
             }
           }
@@ -606,7 +638,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] += old[q];
                   }
-                  store8(p.y + o, v);
+                  if (SPLIT && p.y_f32) store8(p.y_f32 + o, v); else store8(p.y + o, v);
                 }
               }
             }
@@ -710,12 +742,12 @@ static bool pdl_enabled() {
   return v == 1;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool SPLIT = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, MODE>;
   static unsigned long long attr_set = 0;          // one bit per device: function attributes are per device
   if (first_use_on_device(attr_set)) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { attr_set = 0; set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
   }
   int grid = min(p.total_tiles, num_sms());
@@ -730,14 +762,23 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, MODE>, mx, mw, my, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, MODE, SPLIT>, mx, mw, my, p);
   if (e != cudaSuccess) { set_error("conv3x3_tc launch: %s", cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
   return check_launch("conv3x3_tc");
 }
 
+// split-operand launch (fp32 through the bf16 tensor cores): see TcParams
+struct TcSplit {
+  int seg_len, terms, n_pairs;
+  uint32_t seg_map;
+  int planes_out, plane_stride;
+  float* y_f32;
+};
+
 static int conv_tc_common(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, int N,
-                          int H, int W, int Cin, int Cout, int taps, int flags, fosvos_stream_t stream, const char* what) {
-  FOSVOS_REQUIRE(x && w_packed && (y || y_pool) && N > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", what);
+                          int H, int W, int Cin, int Cout, int taps, int flags, fosvos_stream_t stream, const char* what,
+                          const TcSplit* split = nullptr) {
+  FOSVOS_REQUIRE(x && w_packed && (y || y_pool || (split && split->y_f32)) && N > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", what);
   FOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin > 0 && Cout > 0,
                  "%s: Cin=%d and Cout=%d must be positive multiples of 8 (pad the NHWC tensors)", what, Cin, Cout);
   FOSVOS_REQUIRE(!(flags & FOSVOS_CONV_BIAS) || bias, "%s: BIAS flag without bias pointer", what);
@@ -751,11 +792,19 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   p.y_pool = (__nv_bfloat16*)y_pool;
   p.w = (const __nv_bfloat16*)w_packed;
   p.N = N; p.H = H; p.W = W; p.CoutP = Cout;
-  const bool c8 = taps == 9 && Cin == 8 && Cout <= 64 && !getenv("FOSVOS_TC_NO_C8");
+  p.seg_len = split ? split->seg_len : 0;
+  p.seg_map = split ? split->seg_map : 0u;
+  p.split_planes = split ? split->planes_out : 1;
+  p.plane_stride = split ? split->plane_stride : 0;
+  p.y_f32 = split ? split->y_f32 : nullptr;
+  // in split mode `Cin` is the GEMM-K extent per tap (n_pairs segments); the activation tensor holds `terms` segments
+  const int Cact = split ? split->terms * split->seg_len : Cin;
+  const int Cy = split ? split->planes_out * split->plane_stride : Cout;
+  const bool c8 = !split && taps == 9 && Cin == 8 && Cout <= 64 && !getenv("FOSVOS_TC_NO_C8");
   // narrow outputs (side_prep, N = 16) are bound by the MMA issue rate, not by L2 traffic: they keep one ring
   const bool halo = taps == 9 && !c8 && Cout > 32 && !getenv("FOSVOS_TC_NO_HALO");
   // 16 input channels (the side_prep data gradient): one K = 16 MMA per tap instead of a zero-padded 64-channel slab
-  const bool k16 = halo && Cin == 16 && !getenv("FOSVOS_TC_NO_K16");
+  const bool k16 = halo && !split && Cin == 16 && !getenv("FOSVOS_TC_NO_K16");
   p.tw_shift = c8 ? 3 : halo ? pick_tw_shift(H, W, 3, 4) : pick_tw_shift(H, W, 2, 6);
   const int TW = 1 << p.tw_shift, TH = TC_BM >> p.tw_shift;
   p.halo_bytes = (TH + 2) * TW * (k16 ? 32 : 128);
@@ -804,17 +853,27 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   CUtensorMap mx, mw, my;
   int rc = c8     ? encode_c8_map(&mx, x, N, H, W)
            : k16  ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH + 2, 16, true, true)
-           : halo ? encode_act_map(&mx, x, N, H, W, Cin, TW, TH + 2, TC_BK, true)
-                  : encode_act_map(&mx, x, N, H, W, Cin, TW, TH, TC_BK, true);
+           : halo ? encode_act_map(&mx, x, N, H, W, Cact, TW, TH + 2, TC_BK, true)
+                  : encode_act_map(&mx, x, N, H, W, Cact, TW, TH, TC_BK, true);
   if (rc) return rc;
   // output slabs leave through TMA stores (BN >= 64); a pool-only launch (y == nullptr) never issues one: its map
   // just has to encode, so it describes the input tensor
-  rc = y ? encode_act_map(&my, y, N, H, W, Cout, TW, TH, TC_BK, true) : encode_act_map(&my, x, N, H, W, Cin, TW, TH, TC_BK, true);
+  rc = y ? encode_act_map(&my, y, N, H, W, Cy, TW, TH, TC_BK, true) : encode_act_map(&my, x, N, H, W, Cact, TW, TH, TC_BK, true);
   if (rc) return rc;
   rc = encode_w_map(&mw, w_packed, Cout, taps * p.cin_pad, BN, k16);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (c8) return launch_tc<64, MODE_C8>(mx, mw, my, p, st);
+  if (split) {
+    if (halo) {
+      switch (BN) {
+        case 64: return launch_tc<64, MODE_HALO, true>(mx, mw, my, p, st);
+        case 128: return launch_tc<128, MODE_HALO, true>(mx, mw, my, p, st);
+        default: return launch_tc<256, MODE_HALO, true>(mx, mw, my, p, st);
+      }
+    }
+    return BN <= 16 ? launch_tc<16, MODE_GENERIC, true>(mx, mw, my, p, st) : launch_tc<32, MODE_GENERIC, true>(mx, mw, my, p, st);
+  }
   if (k16) {
     switch (BN) {
       case 64: return launch_tc<64, MODE_K16>(mx, mw, my, p, st);
@@ -849,6 +908,35 @@ extern "C" {
 int fosvos_conv3x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, int N, int H,
                       int W, int Cin, int Cout, int flags, fosvos_stream_t stream) {
   return conv_tc_common(x, w_packed, bias, mask, y, nullptr, N, H, W, Cin, Cout, 9, flags, stream, "conv3x3_tc");
+}
+
+int fosvos_split_pairs(int terms) { return terms == 1 ? 1 : terms == 2 ? 3 : terms == 3 ? 6 : -1; }
+
+// products kept for `terms` bf16 terms per operand, in the order the GEMM-K segments are walked (and the weights are packed,
+// fosvos_pack_conv3x3_weight_split): everything above 2^-8 terms relative to x1 * w1
+//   terms 2: x1 w1, x2 w1, x1 w2                      terms 3: + x3 w1, x2 w2, x1 w3
+static const int kSplitActTerm[6] = {0, 1, 0, 2, 1, 0};
+int fosvos_split_weight_term(int terms, int pair) {
+  static const int w_term[6] = {0, 0, 1, 0, 1, 2};
+  return (pair >= 0 && pair < fosvos_split_pairs(terms)) ? w_term[pair] : -1;
+}
+
+int fosvos_conv3x3_tc_split(const void* x, const void* w_packed, const float* bias, void* y, float* y_f32, int N, int H, int W,
+                            int seg_len, int terms, int Cout, int flags, fosvos_stream_t stream) {
+  const int n_pairs = fosvos_split_pairs(terms);
+  FOSVOS_REQUIRE(n_pairs > 0 && seg_len > 0 && seg_len % 64 == 0, "conv3x3_tc_split: terms=%d (1..3), seg_len=%d (a multiple of 64)", terms, seg_len);
+  FOSVOS_REQUIRE(!(flags & (FOSVOS_CONV_MASK | FOSVOS_CONV_ACCUMULATE)), "conv3x3_tc_split: forward epilogues only (BIAS, RELU)");
+  FOSVOS_REQUIRE((y != nullptr) != (y_f32 != nullptr), "conv3x3_tc_split: exactly one of y (split bf16 terms) and y_f32");
+  FOSVOS_REQUIRE(y_f32 ? Cout <= 32 : Cout > 32, "conv3x3_tc_split: fp32 output serves the narrow layers (Cout <= 32), split output the wide ones");
+  FOSVOS_REQUIRE(((uintptr_t)y_f32 & 15) == 0, "conv3x3_tc_split: y_f32 must be 16-byte aligned");
+  TcSplit sp;
+  sp.seg_len = seg_len; sp.terms = terms; sp.n_pairs = n_pairs;
+  sp.seg_map = 0;
+  for (int g = 0; g < n_pairs; ++g) sp.seg_map |= (uint32_t)kSplitActTerm[g] << (4 * g);
+  sp.planes_out = y ? terms : 1;
+  sp.plane_stride = (Cout + 63) / 64 * 64;
+  sp.y_f32 = y_f32;
+  return conv_tc_common(x, w_packed, bias, nullptr, y, nullptr, N, H, W, n_pairs * seg_len, Cout, 9, flags, stream, "conv3x3_tc_split", &sp);
 }
 
 int fosvos_conv3x3_tc_pool(const void* x, const void* w_packed, const float* bias, void* y, void* y_pool, int N, int H, int W,

@@ -26,7 +26,9 @@ from . import ops
 
 
 def _precision_of(m) -> str:
-    return getattr(m, "_fosvos_precision", None) or os.environ.get("FOSVOS_PRECISION", "bf16")
+    p = getattr(m, "_fosvos_precision", None) or os.environ.get("FOSVOS_PRECISION", "bf16")
+    # the split-operand inference modes have no module-level kernels: a leaf called on its own computes in strict fp32
+    return "fp32" if p in ("fp32_tc", "bf16x3") else p
 
 
 def _act_dtype(precision: str) -> torch.dtype:

@@ -10,7 +10,11 @@ convolutions, a fused side-output chain.  There is no CPU path and no cuDNN path
 
 Precision (``net.precision``):
   'bf16'       bf16 activations/weights, fp32 accumulation in TMEM (tcgen05 kernels) -- default
-  'fp32'       fp32 activations/weights, fp32 FMA (direct kernels): the strict-parity mode
+  'fp32'       fp32 activations/weights, fp32 FMA (direct kernels): the strict-parity mode (forward and backward)
+  'fp32_tc'    fp32-equivalent arithmetic on the tcgen05 kernels: every fp32 value travels as three bf16 terms, a product
+               keeps its six significant term products, accumulation is fp32 in TMEM ("bf16x6"; csrc/split.cu) -- the
+               strict-parity mode of INFERENCE on the same kernels the bf16 numbers are measured on
+  'bf16x3'     the same with two terms / three products (16-17 significant bits per operand)
   'bf16_simt'  bf16 data through the direct kernels (debug cross-check of the tcgen05 path)
 """
 from __future__ import annotations
@@ -120,46 +124,81 @@ class OSVOS_VGG(nn.Module):
             self._load_from_caffe()
 
     def _load_from_pytorch(self) -> None:
-        # reference osvos_vgg.py:118-129: copy torchvision VGG-16 conv weights in order
-        from copy import deepcopy
+        """``pretrained=1``: the 13 convolutions of torchvision's ImageNet VGG-16, in order, become the 13 stage
+        convolutions (what reference osvos_vgg.py:118-129 does with deepcopy; needs the torchvision weights on disk)."""
         from torchvision.models import vgg16
-        _vgg = vgg16(pretrained=True)
-        inds = [i for i in range(len(_vgg.features)) if isinstance(_vgg.features[i], nn.Conv2d)]
-        k = 0
-        for i in range(len(self.stages)):
-            for j in range(len(self.stages[i])):
-                if isinstance(self.stages[i][j], nn.Conv2d):
-                    self.stages[i][j].weight = deepcopy(_vgg.features[inds[k]].weight)
-                    self.stages[i][j].bias = deepcopy(_vgg.features[inds[k]].bias)
-                    k += 1
+        donors = [m for m in vgg16(pretrained=True).features if isinstance(m, nn.Conv2d)]
+        ours = [m for stage in self.stages for m in stage if isinstance(m, nn.Conv2d)]
+        if len(donors) != len(ours):
+            raise RuntimeError(f"torchvision VGG-16 has {len(donors)} convolutions, OSVOS stages have {len(ours)}")
+        for dst, src in zip(ours, donors):
+            dst.weight = nn.Parameter(src.weight.detach().clone())
+            dst.bias = nn.Parameter(src.bias.detach().clone())
 
     def _load_from_caffe(self, models_dir: Optional[str] = None) -> None:
-        # reference osvos_vgg.py:139-153 (path from config.mypath there; FOSVOS_MODELS_DIR here)
+        """``pretrained=2``: ``vgg_hed_caffe.mat`` (reference osvos_vgg.py:139-153; its directory comes from
+        ``config.mypath`` there, from ``models_dir`` / ``$FOSVOS_MODELS_DIR`` here).  The file holds one weight array and
+        one bias column per convolution; Caffe stores weights (kW, kH, Cin, Cout), hence the full transpose."""
         import scipy.io
-        models_dir = models_dir or os.environ.get("FOSVOS_MODELS_DIR", ".")
-        caffe_weights = scipy.io.loadmat(os.path.join(models_dir, 'vgg_hed_caffe.mat'))
-        caffe_ind = 0
-        for ind, layer in enumerate(self.stages.parameters()):
-            if ind % 2 == 0:
-                c_w = torch.from_numpy(caffe_weights['weights'][0][caffe_ind].transpose())
-                assert layer.data.shape == c_w.shape
-                layer.data = c_w
-            else:
-                c_b = torch.from_numpy(caffe_weights['biases'][0][caffe_ind][:, 0])
-                assert layer.data.shape == c_b.shape
-                layer.data = c_b
-                caffe_ind += 1
+        mat = scipy.io.loadmat(os.path.join(models_dir or os.environ.get("FOSVOS_MODELS_DIR", "."), 'vgg_hed_caffe.mat'))
+        convs = [m for stage in self.stages for m in stage if isinstance(m, nn.Conv2d)]
+        for k, conv in enumerate(convs):
+            w = torch.from_numpy(mat['weights'][0][k].transpose())
+            b = torch.from_numpy(mat['biases'][0][k][:, 0])
+            if tuple(w.shape) != tuple(conv.weight.shape) or tuple(b.shape) != tuple(conv.bias.shape):
+                raise RuntimeError(f"vgg_hed_caffe.mat: layer {k} holds {tuple(w.shape)} / {tuple(b.shape)}, "
+                                   f"expected {tuple(conv.weight.shape)} / {tuple(conv.bias.shape)}")
+            conv.weight.data = w
+            conv.bias.data = b
 
     # ------------------------------------------------------------------ derived caches
     def _stage_convs(self) -> List[List[nn.Conv2d]]:
         return [[m for m in st if isinstance(m, nn.Conv2d)] for st in self.stages]
+
+    _SPLIT_TERMS = {"fp32_tc": 3, "bf16x3": 2}
 
     def _impl(self) -> str:
         if self.precision == "bf16":
             return "tc"
         if self.precision in ("fp32", "bf16_simt"):
             return "simt"
+        if self.precision in self._SPLIT_TERMS:
+            return "tc_split"
         raise RuntimeError(f"fosvos_b200: unknown precision mode '{self.precision}'")
+
+    def _packed_split_for(self, conv: nn.Conv2d, terms: int) -> _PackedConv:
+        """Split-operand packed weight (one GEMM-K segment per kept term product) + padded bias of one conv, cached."""
+        pc = self._packed.setdefault((id(conv), terms), _PackedConv())
+        b = conv.bias
+        key = (conv.weight.data_ptr(), conv.weight._version, None if b is None else (b.data_ptr(), b._version), terms,
+               tuple(conv.weight.shape))
+        if pc.key != key:
+            same = pc.key is not None and pc.key[3:] == key[3:]
+            pc.w_fwd = ops.pack_weight_split(conv.weight, terms, out=pc.w_fwd if same else None)
+            pc.bias = ops.pad_bias(b, conv.out_channels, conv.weight.device, out=pc.bias if same else None)
+            pc.key = key
+        return pc
+
+    def _run_pipeline_split(self, x: torch.Tensor, want_prob: bool, want_mask: bool):
+        """Inference with fp32-equivalent arithmetic on the tensor cores (precision 'fp32_tc' / 'bf16x3'): split frames ->
+        13 split convs (+ ReLU) and 4 split pools -> side_prep as plain fp32 -> the fp32 side chain."""
+        terms = self._SPLIT_TERMS[self.precision]
+        with torch.cuda.device(x.device):
+            H, W = int(x.shape[-2]), int(x.shape[-1])
+            a = ops.split_frames(x.float(), terms)
+            sps: List[torch.Tensor] = []
+            for si, convs in enumerate(self._stage_convs()):
+                if si > 0:
+                    a = ops.maxpool2x2_split(a, terms)
+                for conv in convs:
+                    pc = self._packed_split_for(conv, terms)
+                    a = ops.conv3x3_split(a, pc.w_fwd, pc.bias, ops.pad8(conv.out_channels), terms, L.CONV_BIAS | L.CONV_RELU)
+                if si > 0:
+                    pc = self._packed_split_for(self.side_prep[si - 1], terms)
+                    sps.append(ops.conv3x3_split(a, pc.w_fwd, pc.bias, 16, terms, L.CONV_BIAS))
+            params = self._side()
+            mode = 1 if self._side_general else (2 if self._side_separable else 0)
+            return ops.side_fwd(sps, params, H, W, general=mode, want_prob=want_prob, want_mask=want_mask)
 
     def _wgrad_impl(self, cin_p: int) -> str:
         # bf16 mode: every layer takes the tensor-core weight gradient, the 3-channel first layer (padded to 8) through
@@ -221,6 +260,18 @@ class OSVOS_VGG(nn.Module):
         ``x``: (N,3,H,W) fp32 mean-subtracted frames (the reference contract), or raw (N,H,W,3) uint8 frames as
         cv2 delivers them -- mean subtraction and layout change then happen in one ingest kernel."""
         L.require_device(x.device)
+        if self._impl() == "tc_split":
+            if save:
+                raise RuntimeError(f"OSVOS_VGG: precision '{self.precision}' is an inference mode (split-operand tensor-core forward); "
+                                   "train with precision 'fp32' (strict) or 'bf16', or call it under torch.no_grad() / net.predict()")
+            if x.dtype == torch.uint8:
+                if x.dim() != 4 or x.shape[3] != 3:
+                    raise RuntimeError(f"OSVOS_VGG: uint8 frames must be (N,H,W,3), got {tuple(x.shape)}")
+                x = ops.nhwc_to_nchw(ops.ingest_u8(x, self.MEANVAL, torch.float32), 3)
+            if x.dim() != 4 or x.shape[1] != self.stages[0][0].in_channels:
+                raise RuntimeError(f"OSVOS_VGG.forward expects (N,{self.stages[0][0].in_channels},H,W), got {tuple(x.shape)}")
+            outs, prob, mask = self._run_pipeline_split(x, want_prob, want_mask)
+            return outs, prob, mask, None
         if x.dtype == torch.uint8:
             if x.dim() != 4 or x.shape[3] != 3 or self.stages[0][0].in_channels != 3:
                 raise RuntimeError(f"OSVOS_VGG: uint8 frames must be (N,H,W,3), got {tuple(x.shape)}")

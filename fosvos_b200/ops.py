@@ -135,6 +135,66 @@ def conv3x3_side(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
     return out
 
 
+# ---- fp32 through the bf16 tensor cores (split operands; csrc/split.cu, conv_tc.cu SPLIT) ---------------------------------
+def seg64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def split_frames(x: torch.Tensor, terms: int) -> torch.Tensor:
+    """NCHW fp32 frames -> split map (N,H,W, terms * seg64(C)) bf16: the bf16 terms of every value side by side."""
+    L.require_device(x.device)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    seg = seg64(c)
+    y = torch.empty((n, h, w, terms * seg), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().fosvos_split_nchw(x.data_ptr(), y.data_ptr(), n, c, h, w, seg, terms, L.stream()), "split_nchw")
+    return y
+
+
+def pack_weight_split(w: torch.Tensor, terms: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """OIHW fp32 (Cout,Cin,3,3) -> the split-operand packed layout (one GEMM-K segment of seg64(Cin) per kept term product)."""
+    L.require_device(w.device)
+    assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
+    w = w.detach().contiguous()
+    cout, cin = int(w.shape[0]), int(w.shape[1])
+    coutp, seg = pad8(cout), seg64(cin)
+    n = L.lib().fosvos_packed_weight_split_elems(coutp, seg, terms)
+    if out is None:
+        out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    assert out.numel() == n and out.dtype == torch.bfloat16
+    L.check(L.lib().fosvos_pack_conv3x3_weight_split(w.data_ptr(), out.data_ptr(), cout, cin, coutp, seg, terms, L.stream()),
+            "pack_conv3x3_weight_split")
+    return out
+
+
+def conv3x3_split(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout_p: int, terms: int, flags: int) -> torch.Tensor:
+    """3x3 conv of a split map on the tensor cores with fp32-equivalent arithmetic.  cout_p > 32: returns the split map of the
+    result (N,H,W, terms * seg64(cout_p)); cout_p <= 32 (side_prep): returns plain fp32 NHWC (N,H,W,cout_p)."""
+    L.require_device(x.device)
+    n, h, w, ct = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and ct % terms == 0
+    seg = ct // terms
+    if cout_p > 32:
+        y = torch.empty((n, h, w, terms * seg64(cout_p)), dtype=torch.bfloat16, device=x.device)
+        yp, yf = y.data_ptr(), None
+    else:
+        y = torch.empty((n, h, w, cout_p), dtype=torch.float32, device=x.device)
+        yp, yf = None, y.data_ptr()
+    L.check(L.lib().fosvos_conv3x3_tc_split(x.data_ptr(), w_packed.data_ptr(), L.ptr(bias), yp, yf, n, h, w, seg, terms, cout_p, flags,
+                                            L.stream()), "conv3x3_tc_split")
+    return y
+
+
+def maxpool2x2_split(x: torch.Tensor, terms: int) -> torch.Tensor:
+    L.require_device(x.device)
+    n, h, w, ct = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and ct % terms == 0
+    y = torch.empty((n, (h + 1) // 2, (w + 1) // 2, ct), dtype=x.dtype, device=x.device)
+    L.check(L.lib().fosvos_maxpool2x2_split(x.data_ptr(), y.data_ptr(), n, h, w, ct // terms, terms, L.stream()), "maxpool2x2_split")
+    return y
+
+
 def wgrad_workspace(cin_p: int, cout_p: int, device) -> torch.Tensor:
     """Zeroed [tap][M][N] fp32 accumulator of the tensor-core weight gradient (kept live across micro-iterations)."""
     return torch.zeros(L.lib().fosvos_conv3x3_wgrad_tc_workspace_bytes(cin_p, cout_p) // 4, dtype=torch.float32, device=device)
@@ -564,7 +624,7 @@ def mask_iou(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # every launching wrapper runs with its tensors' device current (see _lib.on_tensor_device)
-for _name in ("nchw_to_nhwc", "nhwc_to_nchw", "pack_weight", "pad_bias", "conv3x3", "conv3x3_pool", "conv3x3_pool_only", "conv3x3_side",
+for _name in ("nchw_to_nhwc", "nhwc_to_nchw", "pack_weight", "pad_bias", "split_frames", "pack_weight_split", "conv3x3_split", "maxpool2x2_split", "conv3x3", "conv3x3_pool", "conv3x3_pool_only", "conv3x3_side",
               "conv3x3_wgrad_accumulate", "conv3x3_wgrad_finish", "conv3x3_wgrad", "maxpool2x2", "maxpool2x2_bwd", "side_params_prepare",
               "side_check_diagonal", "side_fwd", "side_fwd_heads_done", "side_bwd", "bal_loss_fwd", "bal_loss_fwd_bwd",
               "bal_loss_fwd_bwd_frames", "bal_loss_bwd", "loss_accumulate", "loss_window_finish", "wgrad_fold_all", "repack_all", "sgd_step", "adam_step", "pixel_loss", "taylor_rank", "relu_fwd", "relu_bwd",

@@ -132,6 +132,30 @@ int fosvos_conv3x3_side_tc_supported(int Cin);
 int fosvos_conv3x3_side_tc(const void* x, const void* w_packed, const float* bias, void* y, void* zs,
                            const float* heads, int N, int H, int W, int Cin, fosvos_stream_t stream);
 
+/* ---- fp32 through the bf16 tensor cores (precision 'fp32_tc': the strict-parity mode on tcgen05) ----------------
+ * An fp32 value travels as `terms` bf16 terms x1 = bf16(v), x2 = bf16(v - x1), x3 = bf16(v - x1 - x2) (three terms hold all
+ * 24 bits); a convolution keeps the fosvos_split_pairs(terms) term products above 2^-8*terms relative to x1*w1 (3 for two
+ * terms, 6 for three) and accumulates them in fp32, which reproduces torch's fp32 convolution with TF32 off
+ * (osvos_vgg.py:92 as the reference runs it).  Layout: a split activation map is ONE bf16 NHWC tensor
+ * (N,H,W, terms*seg_len), the terms side by side with seg_len (a multiple of 64, >= C) channels each.
+ *   fosvos_split_nchw: NCHW fp32 frame -> split map (replaces the layout change of fosvos_nchw_to_nhwc).
+ *   fosvos_pack_conv3x3_weight_split: OIHW fp32 -> [CoutP][tap][pairs*seg_len] bf16 whose GEMM-K segment g holds weight
+ *     term fosvos_split_weight_term(terms, g) (fosvos_packed_weight_split_elems elements).
+ *   fosvos_conv3x3_tc_split: 3x3 conv + bias (+ ReLU) of a split map; Cout > 32: y = split map (N,H,W, terms*ceil64(Cout));
+ *     Cout <= 32 (side_prep): y_f32 = plain fp32 NHWC (N,H,W,Cout) for the fp32 side chain.  Exactly one of y / y_f32.
+ *   fosvos_maxpool2x2_split: nn.MaxPool2d(2,2,ceil_mode=True) (osvos_vgg.py:90) on a split map (exact for three terms). */
+int fosvos_split_pairs(int terms);
+int fosvos_split_weight_term(int terms, int pair);
+int fosvos_split_nchw(const float* x_nchw, void* y_split, int N, int C, int H, int W, int seg_len, int terms,
+                      fosvos_stream_t stream);
+long long fosvos_packed_weight_split_elems(int CoutP, int seg_len, int terms);
+int fosvos_pack_conv3x3_weight_split(const float* w_oihw, void* w_packed, int Cout, int Cin, int CoutP, int seg_len,
+                                     int terms, fosvos_stream_t stream);
+int fosvos_conv3x3_tc_split(const void* x_split, const void* w_packed, const float* bias, void* y_split, float* y_f32,
+                            int N, int H, int W, int seg_len, int terms, int Cout, int flags, fosvos_stream_t stream);
+int fosvos_maxpool2x2_split(const void* x_split, void* y_split, int N, int H, int W, int seg_len, int terms,
+                            fosvos_stream_t stream);
+
 /* weight + bias gradient of the same convolution (autograd convolution_backward,
  * train_online.py:93):  dw[co,ci,r,s] += sum_p x[p+tap,ci] * dz[p,co];  db[co] += sum_p dz[p,co]
  * x: (N,H,W,CinP), dz: (N,H,W,CoutP) NHWC; dw: OIHW fp32 (Cout,Cin,3,3) -- the parameter's

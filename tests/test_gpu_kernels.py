@@ -133,6 +133,54 @@ def test_conv3x3_fused_maxpool(case):
     assert torch.equal(yp, p_ref)
 
 
+def _unsplit(y, terms, c):
+    """split map (N,H,W, terms*seg) -> fp32 NCHW of the first c channels: the sum of the bf16 terms"""
+    seg = y.shape[3] // terms
+    return sum(y[..., t * seg:t * seg + c].float() for t in range(terms)).permute(0, 3, 1, 2).cpu()
+
+
+@pytest.mark.parametrize("terms", [3, 2])
+@pytest.mark.parametrize("case", [(1, 9, 11, 3, 64), (2, 12, 10, 64, 128), (1, 17, 23, 128, 256), (1, 8, 8, 72, 40), (1, 7, 9, 128, 16), (2, 5, 30, 512, 16)])
+def test_conv3x3_split_operands(case, terms):
+    """fp32 through the bf16 tensor cores (csrc/split.cu, conv_tc.cu SPLIT): three bf16 terms per operand and six term
+    products reproduce the fp32 convolution (the reference's strict mode) to fp32 rounding; two terms / three products
+    hold ~2^-16.  Cout > 32 returns a split map, Cout <= 32 (side_prep) plain fp32."""
+    n, h, w_, cin, cout = case
+    g = _gen(hash(case) % 1000 + 3)
+    x = torch.randn(n, cin, h, w_, generator=g) * 30.0
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    relu = cout > 32
+    ref = _conv_ref(x, w, b, relu)
+    xs = ops.split_frames(x.to(DEV), terms)
+    assert xs.shape == (n, h, w_, terms * ops.seg64(cin))
+    assert torch.allclose(_unsplit(xs, terms, cin), x, rtol=2.0 ** -23 if terms == 3 else 2.0 ** -15, atol=0)
+    wp = ops.pack_weight_split(w.to(DEV), terms)
+    bp = ops.pad_bias(b.to(DEV), cout, DEV)
+    y = ops.conv3x3_split(xs, wp, bp, ops.pad8(cout), terms, L.CONV_BIAS | (L.CONV_RELU if relu else 0))
+    torch.cuda.synchronize()
+    got = _unsplit(y, terms, cout) if cout > 32 else y[..., :cout].permute(0, 3, 1, 2).cpu()
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert err <= (2e-6 if terms == 3 else 1e-4) * scale, (err, scale)
+    if cout > 32:
+        assert (y.view(n, h, w_, terms, -1)[..., cout:] == 0).all()       # padded lanes of every term stay zero
+
+
+@pytest.mark.parametrize("terms", [3, 2])
+@pytest.mark.parametrize("shape", [(2, 64, 9, 7), (1, 40, 30, 54), (1, 130, 5, 1)])
+def test_maxpool2x2_split(shape, terms):
+    n, c, h, w_ = shape
+    x = torch.randn(shape, generator=_gen(61)) * 10
+    xs = ops.split_frames(x.to(DEV), terms)
+    ys = ops.maxpool2x2_split(xs, terms)
+    x_rep = _unsplit(xs, terms, c)                                         # what the split map holds (exact for three terms)
+    ref = F.max_pool2d(x_rep, 2, 2, ceil_mode=True)
+    got = _unsplit(ys, terms, c)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, rtol=0 if terms == 3 else 2.0 ** -15, atol=0), float((got - ref).abs().max())
+
+
 @pytest.mark.parametrize("case", [(1, 33, 45, 64, 64), (2, 16, 24, 64, 128), (1, 9, 17, 40, 72)])
 def test_conv3x3_pool_only(case):
     """Inference form of the fused pool: the full-resolution output is not written at all (y = NULL); the pooled map is

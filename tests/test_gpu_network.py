@@ -573,3 +573,40 @@ def test_step_graph_follows_param_group_changes():
         d0, d1 = res[0][k] - sd[k], res[1][k] - sd[k]
         assert float(d0.abs().max()) > 0
         assert float((d0 - d1).abs().max()) <= 1e-3 * float(d0.abs().max()) + 1e-12, k
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32_tc", 1e-4), ("bf16x3", None)])
+@pytest.mark.parametrize("name", ["fwd_48x72_random", "fwd_45x70_random", "fwd_64x96_structured"])
+def test_forward_golden_split_operand_modes(name, precision, tol):
+    """fp32-equivalent inference on the tcgen05 kernels (precision 'fp32_tc': three bf16 terms per operand, six products,
+    fp32 accumulation in TMEM) holds the strict 1e-4 bound on the golden fixtures; the two-term mode 'bf16x3' is held to
+    2^-6 of the plain bf16 budget.  Training under these modes is refused loudly."""
+    fix = _load(name + ".pt")
+    x, m, sd = _case(fix)
+    net = _net(sd, precision)
+    outs, prob, mask = net.predict(x.to(DEV))
+    if tol is None:
+        tol = max(1e-4, bf16_budget(sd, x, fix["outs"]) / 64)
+    for o, ref in zip(outs, fix["outs"]):
+        err = float((torch.sigmoid(o.cpu()) - torch.sigmoid(ref)).abs().max())
+        assert err <= tol, (name, precision, err)
+    assert torch.equal(mask.cpu(), O.binarise(prob.cpu()))
+    with pytest.raises(RuntimeError, match="inference mode"):
+        net(x.to(DEV))                                          # grad enabled -> the fused autograd path -> refused
+
+
+def test_full_size_480x854_fp32_tc_against_oracle():
+    """The strict mode on the tensor cores at the benchmark frame size, random weights (the hard case for any reduced
+    precision: tools/bf16_yardstick.py), batch 2."""
+    x = torch.cat([synth.make_frame(0, f, 480, 854)[0] for f in range(2)])
+    xs, ms = synth.make_frame(0, 0, 120, 214)
+    sd = synth.calibrate(synth.make_state_dict(0, "random"), O.vgg_forward, xs)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        ref = O.vgg_forward(sd, x)
+    net = _net(sd, "fp32_tc")
+    outs, prob, mask = net.predict(x.to(DEV))
+    for o, r in zip(outs, ref):
+        err = float((torch.sigmoid(o.cpu()) - torch.sigmoid(r)).abs().max())
+        assert err <= 1e-4, err
+    assert _iou(mask.cpu(), O.binarise(O.probabilities(ref[4]))) >= 0.995
