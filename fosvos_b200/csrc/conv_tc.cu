@@ -124,7 +124,22 @@ struct TcParams {
   int split_planes;              // output terms written by the slab epilogue (1 = plain bf16 output)
   int plane_stride;              // channels between two output terms (a multiple of 64)
   float* y_f32;                  // narrow epilogue (BN <= 32): fp32 output instead of bf16 (or null)
+  // The tensor core chops (does not round) when it adds into its fp32 accumulator: ~2^-25 relative per MMA, same sign every
+  // time, so a K-long chain loses (K / 16) * 2^-25 -- invisible next to a bf16 result, but 1e-5 .. 3e-5 per layer for a
+  // split-operand convolution.  Split launches therefore keep FOUR accumulators per tile: the leading products x1 w1 alternate
+  // between two by 64-channel slab parity (half the chain each), the first-order products (x2 w1, x1 w2; 2^-8 smaller, so their
+  // chopping error is too) take the third, the second-order ones the fourth; the epilogue adds them in fp32, smallest first.
+  uint32_t ord_map;              // order (0, 1, 2) of GEMM-K segment g in bits [4g, 4g + 4)
+  uint32_t acc_used;             // bit a: accumulator a receives at least one MMA per tile
 };
+
+// accumulator (0..3) of 64-channel K slab `ks` in a split launch
+__device__ __forceinline__ int tc_acc_id(const TcParams& p, int ks) {
+  const int per = p.seg_len >> 6;
+  const int g = ks / per;
+  const int ord = (int)((p.ord_map >> (4 * g)) & 15u);
+  return ord == 0 ? ((ks - g * per) & 1) : ord + 1;
+}
 
 // activation channel of GEMM-K position c (a multiple of 64) in split-operand mode
 __device__ __forceinline__ int tc_act_chan(const TcParams& p, int c) {
@@ -193,7 +208,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  constexpr int ACC_STRIDE = SPLIT ? 4 * BN : BN;                          // TMEM columns of one accumulator stage
+  constexpr int TMEM_COLS = SPLIT ? (8 * BN < 32 ? 32 : 8 * BN) : Cfg::TMEM_COLS;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
+  if (warp == 1) ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
   // everything above overlaps the tail of the previous kernel under programmatic dependent launch; global
   // memory is only touched after the wait
   ptx::griddep_launch_dependents();
@@ -339,7 +357,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);      // the epilogue group has drained this accumulator
       ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * BN;
+      const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
+      uint32_t started = 0;                                 // SPLIT: accumulators that already hold a partial sum of this tile
+      (void)started;
       if constexpr (MODE == MODE_C8) {
         ptx::mbar_wait_a(bar_full, phase);
         ptx::tc_fence_after();
@@ -369,6 +389,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         uint32_t acc = 0;
         for (int bx = 0; bx < n_boxes; ++bx) {
           ptx::mbar_wait_a(bar_full, phase);                // halo box has landed
+          uint32_t tmem_t = tmem_d;                         // SPLIT: the accumulator of this K slab (boxes walk slab-major: bx / 3)
+          if constexpr (SPLIT) {
+            const int a_id = tc_acc_id(p, bx / 3);
+            tmem_t = tmem_d + a_id * BN;
+            acc = (started >> a_id) & 1u;
+            started |= 1u << a_id;
+          }
           for (int r = 0; r < 3; r += Cfg::B_GROUP) {
             ptx::mbar_wait_a(bbar_full, bphase);            // weight tile(s) of tap(s) (r.., s) have landed
             ptx::tc_fence_after();
@@ -377,7 +404,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               for (int g = 0; g < Cfg::B_GROUP; ++g) {
 #pragma unroll
                 for (int k = 0; k < K_STEPS; ++k) {
-                  ptx::umma_bf16_lohi(tmem_d, a_lo + (r + g) * tap_step + 2 * k, b_lo + g * (Cfg::B_BYTES >> 4) + 2 * k, desc_hi, idesc,
+                  ptx::umma_bf16_lohi(tmem_t, a_lo + (r + g) * tap_step + 2 * k, b_lo + g * (Cfg::B_BYTES >> 4) + 2 * k, desc_hi, idesc,
                                       acc | g | k);
                 }
               }
@@ -408,10 +435,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             for (int g = 0; g < Cfg::K_GROUP; ++g) {
               if (g < ng) {
                 const uint32_t a_g = a_lo + g * ((Cfg::A_BYTES + Cfg::B_BYTES) >> 4);
+                uint32_t tmem_t = tmem_d, first = (uint32_t)(kb | g);
+                if constexpr (SPLIT) {                    // the accumulator of K slab in_tap * K_GROUP + g
+                  const int a_id = tc_acc_id(p, in_tap * Cfg::K_GROUP + g);
+                  tmem_t = tmem_d + a_id * BN;
+                  first = (started >> a_id) & 1u;
+                  started |= 1u << a_id;
+                }
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
                   // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-                  ptx::umma_bf16_lohi(tmem_d, a_g + 2 * k, a_g + (Cfg::A_BYTES >> 4) + 2 * k, desc_hi, idesc, (kb | g | k) != 0);
+                  ptx::umma_bf16_lohi(tmem_t, a_g + 2 * k, a_g + (Cfg::A_BYTES >> 4) + 2 * k, desc_hi, idesc, (first | k) != 0);
                 }
               }
             }
@@ -482,7 +516,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (mask_slab) load_mask(n0);
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * ACC_STRIDE;
       if constexpr (Cfg::STAGED) {
         // 64-channel slabs: TMEM -> registers -> bias/ReLU/mask/accumulate -> bf16 -> swizzled smem -> one TMA store
         // (the store clips the patch at the frame edge and the channel tail)
@@ -496,8 +530,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           uint32_t packed[16];
           if (live) {
             uint32_t r[32];
-            ptx::tmem_ld32(taddr + 64 * j + 32 * half, r);
-            ptx::tmem_ld_wait();
+            if constexpr (SPLIT) {
+              // the four partial accumulators of the tile, added in fp32 smallest first (second order, first order, the
+              // two halves of the leading products)
+              bool have = false;
+#pragma unroll
+              for (int a = 3; a >= 0; --a) {
+                if ((p.acc_used >> a) & 1u) {
+                  uint32_t t[32];
+                  ptx::tmem_ld32(taddr + a * BN + 64 * j + 32 * half, t);
+                  ptx::tmem_ld_wait();
+#pragma unroll
+                  for (int q = 0; q < 32; ++q) r[q] = have ? __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(t[q])) : t[q];
+                  have = true;
+                }
+              }
+            } else {
+              ptx::tmem_ld32(taddr + 64 * j + 32 * half, r);
+              ptx::tmem_ld_wait();
+            }
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int co = co0 + 32 * half + 8 * h;    // < 512: bias_s holds zeros past CoutP
@@ -612,8 +663,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 16) {
             uint32_t r[16];
-            ptx::tmem_ld16(taddr + c0, r);
-            ptx::tmem_ld_wait();
+            if constexpr (SPLIT) {
+              bool have = false;
+#pragma unroll
+              for (int a = 3; a >= 0; --a) {
+                if ((p.acc_used >> a) & 1u) {
+                  uint32_t t[16];
+                  ptx::tmem_ld16(taddr + a * BN + c0, t);
+                  ptx::tmem_ld_wait();
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) r[q] = have ? __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(t[q])) : t[q];
+                  have = true;
+                }
+              }
+            } else {
+              ptx::tmem_ld16(taddr + c0, r);
+              ptx::tmem_ld_wait();
+            }
             if (in_img) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -656,7 +722,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -797,6 +863,12 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   p.split_planes = split ? split->planes_out : 1;
   p.plane_stride = split ? split->plane_stride : 0;
   p.y_f32 = split ? split->y_f32 : nullptr;
+  p.ord_map = 0; p.acc_used = 1;
+  if (split) {
+    static const int order[6] = {0, 1, 1, 2, 2, 2};
+    for (int g = 0; g < split->n_pairs; ++g) p.ord_map |= (uint32_t)order[g] << (4 * g);
+    p.acc_used = 1u | (split->seg_len > 64 ? 2u : 0u) | (split->terms >= 2 ? 4u : 0u) | (split->terms >= 3 ? 8u : 0u);
+  }
   // in split mode `Cin` is the GEMM-K extent per tap (n_pairs segments); the activation tensor holds `terms` segments
   const int Cact = split ? split->terms * split->seg_len : Cin;
   const int Cy = split ? split->planes_out * split->plane_stride : Cout;
@@ -835,6 +907,7 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   }
   if (const char* e = getenv("FOSVOS_TC_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && (v & (v - 1)) == 0) BN = v; }
   if (c8) BN = 64;
+  if (split && BN > 64) BN = 64;          // four accumulators per tile and two tiles in flight: 8 x 64 = the 512 TMEM columns
   p.n_tiles_n = ceil_div(Cout, BN);
   {
     auto fd = [](int d, uint32_t& mul, uint32_t& shift) {
@@ -865,13 +938,7 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   cudaStream_t st = as_stream(stream);
   if (c8) return launch_tc<64, MODE_C8>(mx, mw, my, p, st);
   if (split) {
-    if (halo) {
-      switch (BN) {
-        case 64: return launch_tc<64, MODE_HALO, true>(mx, mw, my, p, st);
-        case 128: return launch_tc<128, MODE_HALO, true>(mx, mw, my, p, st);
-        default: return launch_tc<256, MODE_HALO, true>(mx, mw, my, p, st);
-      }
-    }
+    if (halo) return launch_tc<64, MODE_HALO, true>(mx, mw, my, p, st);
     return BN <= 16 ? launch_tc<16, MODE_GENERIC, true>(mx, mw, my, p, st) : launch_tc<32, MODE_GENERIC, true>(mx, mw, my, p, st);
   }
   if (k16) {

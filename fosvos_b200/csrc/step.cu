@@ -8,7 +8,7 @@
 
 namespace fosvos {
 
-constexpr int FOLD_CO = 8, FOLD_CI = 32;            // tile: 8 couts x 32 cins x 9 taps
+constexpr int FOLD_CO = 32, FOLD_CI = 32;           // tile: 32 couts x 32 cins x 9 taps (36 KB in flight per block)
 constexpr int PACK_CO = 32, PACK_CI = 32;           // tile: 32 couts x 32 cins x 9 taps
 
 // tile t of the flat list belongs to entry e with prefix[e] <= t < prefix[e + 1]
@@ -23,7 +23,9 @@ __device__ __forceinline__ int find_entry(const int* __restrict__ prefix, int n,
 
 __global__ void __launch_bounds__(256)
 wgrad_fold_kernel(const fosvos_fold_entry* __restrict__ table, int n_entries, const int* __restrict__ prefix, int n_tiles) {
-  __shared__ float sm[FOLD_CO * FOLD_CI * 9];
+  // row pitch FOLD_CI * 9 + 1 (odd): the gather below writes columns of this array when the workspace is [tap][cin][cout]
+  constexpr int FPITCH = FOLD_CI * 9 + 1;
+  __shared__ float sm[FOLD_CO * FPITCH];
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int ei = find_entry(prefix, n_entries, tile);
     const fosvos_fold_entry e = table[ei];
@@ -40,7 +42,7 @@ wgrad_fold_kernel(const fosvos_fold_entry* __restrict__ table, int n_entries, co
       if (co_l < nco && ci_l < nci) {
         const int co = co0 + co_l, ci = ci0 + ci_l;
         float* src = e.ws + tap * plane + (e.x_is_a ? ((long long)ci * e.CoutP + co) : ((long long)co * e.CinP + ci));
-        sm[(co_l * FOLD_CI + ci_l) * 9 + tap] = *src;
+        sm[co_l * FPITCH + ci_l * 9 + tap] = *src;
         *src = 0.f;
       }
     }
@@ -49,7 +51,7 @@ wgrad_fold_kernel(const fosvos_fold_entry* __restrict__ table, int n_entries, co
     const int run = nci * 9;
     for (int i = threadIdx.x; i < nco * run; i += 256) {
       const int co_l = i / run, r = i - co_l * run;
-      e.dw[((long long)(co0 + co_l) * e.Cin + ci0) * 9 + r] += sm[co_l * FOLD_CI * 9 + r];
+      e.dw[((long long)(co0 + co_l) * e.Cin + ci0) * 9 + r] += sm[co_l * FPITCH + r];
     }
     __syncthreads();
   }
@@ -77,19 +79,34 @@ repack_kernel(const fosvos_repack_entry* __restrict__ table, int n_entries, cons
     __nv_bfloat16* fwd = reinterpret_cast<__nv_bfloat16*>(e.out_fwd);
     __nv_bfloat16* dgr = reinterpret_cast<__nv_bfloat16*>(e.out_dgrad);
     if (fwd) {
-      // [co][tap][pad_ci]: ci fastest
-      for (int i = threadIdx.x; i < nco * 9 * PACK_CI; i += 256) {
-        const int ci_l = i % PACK_CI, tap = (i / PACK_CI) % 9, co_l = i / (PACK_CI * 9);
-        if (ci_l < nci)
-          fwd[((long long)(co0 + co_l) * 9 + tap) * e.pad_ci + ci0 + ci_l] = __float2bfloat16_rn(sm[co_l * PITCH + ci_l * 9 + tap]);
+      // [co][tap][pad_ci]: ci fastest; a thread writes eight consecutive cins as one 16-byte store (pad_ci and ci0 are
+      // multiples of 32, so the address is aligned); channels past the weight's Cin keep their zero padding
+      for (int i = threadIdx.x; i < nco * 9 * (PACK_CI / 8); i += 256) {
+        const int c8 = i % (PACK_CI / 8), tap = (i / (PACK_CI / 8)) % 9, co_l = i / ((PACK_CI / 8) * 9);
+        __nv_bfloat16* dst = fwd + ((long long)(co0 + co_l) * 9 + tap) * e.pad_ci + ci0 + 8 * c8;
+        if (8 * c8 + 8 <= nci) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = sm[co_l * PITCH + (8 * c8 + q) * 9 + tap];
+          store8(dst, v);
+        } else {
+          for (int q = 0; 8 * c8 + q < nci; ++q) dst[q] = __float2bfloat16_rn(sm[co_l * PITCH + (8 * c8 + q) * 9 + tap]);
+        }
       }
     }
     if (dgr) {
-      // [ci][8 - tap][pad_co]: co fastest
-      for (int i = threadIdx.x; i < nci * 9 * PACK_CO; i += 256) {
-        const int co_l = i % PACK_CO, tap = (i / PACK_CO) % 9, ci_l = i / (PACK_CO * 9);
-        if (co_l < nco)
-          dgr[((long long)(ci0 + ci_l) * 9 + (8 - tap)) * e.pad_co + co0 + co_l] = __float2bfloat16_rn(sm[co_l * PITCH + ci_l * 9 + tap]);
+      // [ci][8 - tap][pad_co]: co fastest, eight consecutive couts per 16-byte store
+      for (int i = threadIdx.x; i < nci * 9 * (PACK_CO / 8); i += 256) {
+        const int c8 = i % (PACK_CO / 8), tap = (i / (PACK_CO / 8)) % 9, ci_l = i / ((PACK_CO / 8) * 9);
+        __nv_bfloat16* dst = dgr + ((long long)(ci0 + ci_l) * 9 + (8 - tap)) * e.pad_co + co0 + 8 * c8;
+        if (8 * c8 + 8 <= nco) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = sm[(8 * c8 + q) * PITCH + ci_l * 9 + tap];
+          store8(dst, v);
+        } else {
+          for (int q = 0; 8 * c8 + q < nco; ++q) dst[q] = __float2bfloat16_rn(sm[(8 * c8 + q) * PITCH + ci_l * 9 + tap]);
+        }
       }
     }
     __syncthreads();

@@ -162,7 +162,10 @@ def test_conv3x3_split_operands(case, terms):
     got = _unsplit(y, terms, cout) if cout > 32 else y[..., :cout].permute(0, 3, 1, 2).cpu()
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
-    assert err <= (2e-6 if terms == 3 else 1e-4) * scale, (err, scale)
+    # three terms: what is left is the tensor core's chopped fp32 accumulation (~2^-25 per MMA of the longest accumulator
+    # chain: the kernel spreads a tile over four accumulators and adds them in the epilogue)
+    print(f"split conv {case} terms {terms}: max err {err:.3e} = {err / scale:.2e} of the map scale")
+    assert err <= (8e-6 if terms == 3 else 1e-4) * scale, (err, scale)
     if cout > 32:
         assert (y.view(n, h, w_, terms, -1)[..., cout:] == 0).all()       # padded lanes of every term stay zero
 
