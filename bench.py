@@ -625,12 +625,14 @@ def gpu_reference(sd, frames_d, masks_d, args, ours_job_s):
                         e1.record(); torch.cuda.synchronize()
                     res[f"inference_fps_batch{bs}"] = n_batches * bs / (e0.elapsed_time(e1) / 1e3)
                 x, m = frames_d[0:1], masks_d[0:1]
-                _stock_finetune(sd_d, x, m, 5, 5, prep)             # warm-up: autotune, allocator
+                _stock_finetune(sd_d, x, m, 10, 5, prep)            # warm-up: autotune, allocator
                 torch.cuda.synchronize()
-                n_it = 10
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); _stock_finetune(sd_d, x, m, n_it, 5, prep); e1.record(); torch.cuda.synchronize()
-                res["finetune_ms_per_iter"] = e0.elapsed_time(e1) / n_it
+                n_it, best_ms = 10, float("inf")
+                for _ in range(3):                                  # best of three: cuDNN's autotuned picks settle after a few calls
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); _stock_finetune(sd_d, x, m, n_it, 5, prep); e1.record(); torch.cuda.synchronize()
+                    best_ms = min(best_ms, e0.elapsed_time(e1) / n_it)
+                res["finetune_ms_per_iter"] = best_ms
             job = args.iters * res["finetune_ms_per_iter"] / 1e3 + args.frames / res[f"inference_fps_batch{args.batch}"]
             res["job_frames_per_s_extrapolated"] = args.frames / job
             res["job_s_extrapolated"] = job
@@ -641,8 +643,8 @@ def gpu_reference(sd, frames_d, masks_d, args, ours_job_s):
             out[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         torch.cuda.empty_cache()
     out["best"] = best
-    out["sample"] = (f"per variant: 8 frames at batch 1 + 3 batches of {args.batch} (2 discarded warm-up batches each), 10 fine-tune "
-                     f"iterations (2 optimizer steps) after 5 warm-up iterations; job extrapolated linearly to {args.iters} iterations + {args.frames} frames")
+    out["sample"] = (f"per variant: 8 frames at batch 1 + 3 batches of {args.batch} (2 discarded warm-up batches each), best of 3 x 10 fine-tune "
+                     f"iterations (2 optimizer steps each) after 10 warm-up iterations; job extrapolated linearly to {args.iters} iterations + {args.frames} frames")
     if best is not None and ours_job_s:
         out["ours_over_best"] = out[best]["job_s_extrapolated"] / ours_job_s
     out["what"] = "oracle/osvos_oracle.py (the reference's torch.nn.functional calls) + autograd + torch.optim.SGD on CUDA tensors; stock PyTorch %s / cuDNN %s" % (torch.__version__, torch.backends.cudnn.version())

@@ -51,6 +51,7 @@ SIGNATURES = {
     "fosvos_conv3x3_wgrad_tc_orientation": (_i, [_i, _i]),
     "fosvos_fold_tile_count": (_i, [_i, _i]),
     "fosvos_repack_tile_count": (_i, [_i, _i]),
+    "fosvos_conv_step_all": (_i, [_vp, _i, _vp, _i, _f, _vp]),
     "fosvos_wgrad_fold_all": (_i, [_vp, _i, _vp, _i, _vp]),
     "fosvos_repack_all": (_i, [_vp, _i, _vp, _i, _vp]),
     "fosvos_adam_chunk_elems": (_i, []),

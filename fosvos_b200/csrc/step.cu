@@ -113,11 +113,102 @@ repack_kernel(const fosvos_repack_entry* __restrict__ table, int n_entries, cons
   }
 }
 
+// The whole optimizer step of a 3x3 conv weight in ONE pass over its data (fold + SGD + repack fused): per 32 x 32 x 9 tile
+//   g = ws[tap][M][N] (+ .grad, when the caller keeps one);  ws = 0 (.grad = 0)
+//   buf = mu * buf + (g + wd * p);  p -= lr * buf                      (torch.optim.SGD, train_online.py:99-100)
+//   packed bf16 forward / data-gradient copies and the padded bias refreshed from the new p
+// Moves 28 B per parameter (ws read + zeroed, p and buf read + written, 2 x 2 B packed) instead of the 48 B of the three
+// separate launches.
+__global__ void __launch_bounds__(256)
+conv_step_kernel(const fosvos_convstep_entry* __restrict__ table, int n_entries, const int* __restrict__ prefix, int n_tiles, float mu) {
+  constexpr int PITCH = PACK_CI * 9 + 1;
+  __shared__ float sm[PACK_CO * PITCH];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int ei = find_entry(prefix, n_entries, tile);
+    const fosvos_convstep_entry e = table[ei];
+    const int local = tile - __ldg(prefix + ei);
+    const int ci_tiles = (e.Cin + PACK_CI - 1) / PACK_CI;
+    const int co0 = (local / ci_tiles) * PACK_CO, ci0 = (local % ci_tiles) * PACK_CI;
+    const int nco = min(PACK_CO, e.Cout - co0), nci = min(PACK_CI, e.Cin - ci0);
+    const long long plane = (long long)e.CoutP * e.CinP;
+    // 1. gather the accumulator tile (fastest index = the workspace's contiguous dimension) and clear it
+    for (int i = threadIdx.x; i < 9 * PACK_CO * PACK_CI; i += 256) {
+      int tap, co_l, ci_l;
+      if (e.x_is_a) { co_l = i % PACK_CO; ci_l = (i / PACK_CO) % PACK_CI; tap = i / (PACK_CO * PACK_CI); }
+      else          { ci_l = i % PACK_CI; co_l = (i / PACK_CI) % PACK_CO; tap = i / (PACK_CO * PACK_CI); }
+      if (co_l < nco && ci_l < nci) {
+        const int co = co0 + co_l, ci = ci0 + ci_l;
+        float* src = e.ws + tap * plane + (e.x_is_a ? ((long long)ci * e.CoutP + co) : ((long long)co * e.CinP + ci));
+        sm[co_l * PITCH + ci_l * 9 + tap] = *src;
+        *src = 0.f;
+      }
+    }
+    __syncthreads();
+    // 2. SGD with momentum over the OIHW runs (nci * 9 contiguous floats per cout); the new weights replace the gradient in smem
+    const int run = nci * 9;
+    const float lr = e.lr, wd = e.weight_decay;
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+      const int co_l = i / run, r = i - co_l * run;
+      const long long gi = ((long long)(co0 + co_l) * e.Cin + ci0) * 9 + r;
+      float gv = sm[co_l * PITCH + r];
+      if (e.dw) { gv += e.dw[gi]; e.dw[gi] = 0.f; }
+      float pv = e.w[gi];
+      const float bv = mu * e.buf[gi] + (gv + wd * pv);
+      e.buf[gi] = bv;
+      pv -= lr * bv;
+      e.w[gi] = pv;
+      sm[co_l * PITCH + r] = pv;
+    }
+    if (ci0 == 0 && e.bias_out && threadIdx.x < nco)
+      e.bias_out[co0 + threadIdx.x] = e.bias ? e.bias[co0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    // 3. packed copies (as repack_kernel)
+    __nv_bfloat16* fwd = reinterpret_cast<__nv_bfloat16*>(e.out_fwd);
+    __nv_bfloat16* dgr = reinterpret_cast<__nv_bfloat16*>(e.out_dgrad);
+    if (fwd) {
+      for (int i = threadIdx.x; i < nco * 9 * (PACK_CI / 8); i += 256) {
+        const int c8 = i % (PACK_CI / 8), tap = (i / (PACK_CI / 8)) % 9, co_l = i / ((PACK_CI / 8) * 9);
+        __nv_bfloat16* dst = fwd + ((long long)(co0 + co_l) * 9 + tap) * e.pad_ci + ci0 + 8 * c8;
+        if (8 * c8 + 8 <= nci) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = sm[co_l * PITCH + (8 * c8 + q) * 9 + tap];
+          store8(dst, v);
+        } else {
+          for (int q = 0; 8 * c8 + q < nci; ++q) dst[q] = __float2bfloat16_rn(sm[co_l * PITCH + (8 * c8 + q) * 9 + tap]);
+        }
+      }
+    }
+    if (dgr) {
+      for (int i = threadIdx.x; i < nci * 9 * (PACK_CO / 8); i += 256) {
+        const int c8 = i % (PACK_CO / 8), tap = (i / (PACK_CO / 8)) % 9, ci_l = i / ((PACK_CO / 8) * 9);
+        __nv_bfloat16* dst = dgr + ((long long)(ci0 + ci_l) * 9 + (8 - tap)) * e.pad_co + co0 + 8 * c8;
+        if (8 * c8 + 8 <= nco) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = sm[(8 * c8 + q) * PITCH + ci_l * 9 + tap];
+          store8(dst, v);
+        } else {
+          for (int q = 0; 8 * c8 + q < nco; ++q) dst[q] = __float2bfloat16_rn(sm[(8 * c8 + q) * PITCH + ci_l * 9 + tap]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace fosvos
 
 using namespace fosvos;
 
 extern "C" {
+
+int fosvos_conv_step_all(const fosvos_convstep_entry* table, int n_entries, const int* tile_prefix, int n_tiles, float momentum,
+                         fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(table && tile_prefix && n_entries > 0 && n_tiles > 0, "conv_step_all: bad arguments");
+  conv_step_kernel<<<min(n_tiles, num_sms() * 6), 256, 0, as_stream(stream)>>>(table, n_entries, tile_prefix, n_tiles, momentum);
+  return check_launch("conv_step_all");
+}
 
 int fosvos_fold_tile_count(int Cout, int Cin) { return ceil_div(Cout, FOLD_CO) * ceil_div(Cin, FOLD_CI); }
 int fosvos_repack_tile_count(int Cout, int Cin) { return ceil_div(Cout, PACK_CO) * ceil_div(Cin, PACK_CI); }

@@ -39,13 +39,16 @@ def _on_device(fn):
 MAX_RESIDENT_TRAINERS = 6        # 3 train-time scales x {plain, flipped} share a size: 6 covers every shape of SURVEY section 7 step 5
 
 
-def _repack_in_place(net: OSVOS_VGG) -> None:
+def _repack_in_place(net: OSVOS_VGG, weights: bool = True) -> None:
     """Refresh the packed weight copies INTO their existing buffers (their addresses are baked into
-    captured graphs) after the parameters changed.  Tensor-core mode: one launch for all layers."""
+    captured graphs) after the parameters changed.  Tensor-core mode: one launch for all layers.
+    ``weights=False``: the conv weights were re-packed by the fused optimizer step; only the side-chain block is rebuilt."""
     dt = _act_dtype(net.precision)
     tc = net._impl() == "tc"
     convs = [c for st in net._stage_convs() for c in st] + list(net.side_prep)
-    if tc:
+    if not weights:
+        pass
+    elif tc:
         ent = []
         for conv in convs:
             pc = net._packed.get(id(conv))
@@ -192,7 +195,14 @@ class OnlineTrainer:
                     if name.endswith(".weight") and params[name].dim() == 4 and tuple(params[name].shape[2:]) == (3, 3):
                         cout, cin = params[name].shape[0], params[name].shape[1]
                         wgrad_ws[name[:-len(".weight")]] = ops.wgrad_workspace(ops.pad8(cin), ops.pad8(cout), dev)
+            # single-GPU tensor-core fine-tune: fold + SGD + repack of the 3x3 conv weights are ONE fused launch per step
+            # (step.cu: conv_step_kernel); the optimizer keeps the biases and the heads
+            import os as _os
+            conv_step = self.fused and wgrad_ws is not None and not self.data_parallel and _os.environ.get("FOSVOS_FUSED_STEP", "1") != "0"
+            if conv_step:
+                self.optimizer.exclude([params[name + ".weight"] for name in wgrad_ws])
             self._shared = dict(optimizer=self.optimizer, grads=grads, flat_grad=flat_grad, buckets=buckets, wgrad_ws=wgrad_ws,
+                                conv_step=conv_step, conv_table=None, conv_key=None,
                                 fold_table=None, step_graph=None, calls_step=0, step_gen=-1, counter=0,
                                 loss_sum=torch.zeros((), dtype=torch.float32, device=dev),
                                 last_loss=torch.zeros((), dtype=torch.float32, device=dev))
@@ -307,7 +317,33 @@ class OnlineTrainer:
                 ops.wgrad_fold_all(tab)
             self._ar_works.append(bk.allreduce(bucket))
 
+    def _ensure_conv_table(self) -> None:
+        """Device table of the fused conv-weight step; rewritten IN PLACE when a learning rate, weight decay or buffer changed
+        (captured step graphs read it at replay)."""
+        sh = self._shared
+        if sh.get("conv_static") is None:
+            params = dict(self.net.named_parameters())
+            modules = dict(self.net.named_modules())
+            groups = {id(q): g for g in self.optimizer.param_groups for q in g["params"]}
+            sh["conv_static"] = [(ws, modules[name], params[name + ".weight"], groups[id(params[name + ".weight"])])
+                                 for name, ws in self.wgrad_ws.items()]
+        ent = []
+        for ws, conv, w, grp in sh["conv_static"]:
+            pc = self.net._packed_for(conv, need_dgrad=True)
+            ent.append((ws, None, w.detach(), self.optimizer.momentum_buffer(w), None if conv.bias is None else conv.bias.detach(),
+                        pc.w_fwd, pc.w_dgrad, pc.bias, float(grp["lr"]), float(grp["weight_decay"])))
+        key = tuple((e[0].data_ptr(), e[2].data_ptr(), e[3].data_ptr(), 0 if e[4] is None else e[4].data_ptr(), e[5].data_ptr(),
+                     0 if e[6] is None else e[6].data_ptr(), e[7].data_ptr(), e[8], e[9]) for e in ent)
+        if key != sh["conv_key"]:
+            old = sh["conv_table"]
+            sh["conv_table"] = ops.convstep_table(ent, self.device, out=old)
+            if old is not None and sh["conv_table"] is not old:
+                sh["step_gen"] = -1                      # a new table address: the captured step must be re-captured
+            sh["conv_key"] = key
+
     def _fold_wgrads(self) -> None:
+        if self._shared["conv_step"]:
+            return                                       # the fused step consumes the accumulators directly
         if self.wgrad_ws:
             if self._fold_table is None:
                 self._fold_table = ops.fold_table([(ws, self.grads[name + ".weight"]) for name, ws in self.wgrad_ws.items()],
@@ -322,7 +358,15 @@ class OnlineTrainer:
     def _step(self) -> None:
         """optimizer.step(); optimizer.zero_grad() (+ re-packing).  The caller has folded the weight-gradient
         accumulators (and all-reduced the gradients) before."""
-        if self.fused:
+        if self.fused and self._shared["conv_step"]:
+            self.optimizer.step_and_zero()               # biases and heads (the conv weights are excluded)
+            if self._shared["conv_table"] is None:
+                self._ensure_conv_table()
+            ops.conv_step_all(self._shared["conv_table"], self.optimizer._momentum)
+            for _, _, w, _ in self._shared["conv_static"]:
+                torch.autograd.graph.increment_version(w)
+            _repack_in_place(self.net, weights=False)
+        elif self.fused:
             self.optimizer.step_and_zero()
             _repack_in_place(self.net)
         else:
@@ -361,6 +405,8 @@ class OnlineTrainer:
                 self._fold_table = ops.fold_table([(ws, self.grads[name + ".weight"]) for name, ws in self.wgrad_ws.items()],
                                                   self.frame.device)
             _repack_in_place(self.net)              # builds the multi-tensor repack table (host -> device copies)
+            if self._shared["conv_step"]:
+                self._ensure_conv_table()
         torch.cuda.current_stream().wait_stream(s)
         graph = torch.cuda.CUDAGraph()
         pool = next((g.pool() for g in (self._micro_graph, self._window_graph, self._step_graph) if g is not None), None)   # one pool per network
@@ -382,6 +428,8 @@ class OnlineTrainer:
 
     def _capture_step(self, pool=None) -> None:
         self.optimizer._ensure_table()
+        if self._shared["conv_step"]:
+            self._ensure_conv_table()
         c0 = L.CALLS[0]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, **({} if pool is None else {"pool": pool})):
@@ -452,6 +500,8 @@ class OnlineTrainer:
             # param_groups (lr, weight decay) or momentum buffers changed since the capture?  The device table is rewritten
             # in place; only a new geometry / momentum needs a fresh capture of the step
             self.optimizer._ensure_table()
+            if self._shared["conv_step"]:
+                self._ensure_conv_table()
             if self._step_graph is None or self._shared["step_gen"] != self.optimizer._table_gen:
                 self._capture_step(next((g.pool() for g in (self._micro_graph, self._window_graph) if g is not None), None))
             self._step_graph.replay()

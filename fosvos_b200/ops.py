@@ -492,6 +492,44 @@ def repack_table(entries, device):
     return _tile_table(tab, counts, device)
 
 
+CONVSTEP_ENTRY = np.dtype([("ws", np.uint64), ("dw", np.uint64), ("w", np.uint64), ("buf", np.uint64), ("bias", np.uint64),
+                           ("out_fwd", np.uint64), ("out_dgrad", np.uint64), ("bias_out", np.uint64),
+                           ("Cout", np.int32), ("Cin", np.int32), ("CoutP", np.int32), ("CinP", np.int32),
+                           ("x_is_a", np.int32), ("pad_ci", np.int32), ("pad_co", np.int32), ("pad_", np.int32),
+                           ("lr", np.float32), ("wd", np.float32)])
+
+
+def convstep_table(entries, device, out=None):
+    """entries: (ws, dw or None, weight, momentum buffer, bias or None, packed fwd, packed dgrad or None, padded bias, lr, wd)
+    per conv -> device table for ``conv_step_all``.  ``out``: an existing table of the same geometry to rewrite in place."""
+    assert CONVSTEP_ENTRY.itemsize == 104
+    tab = np.zeros(len(entries), dtype=CONVSTEP_ENTRY)
+    counts = []
+    for i, (ws, dw, w, buf, b, fwd, dgr, bo, lr, wd) in enumerate(entries):
+        cout, cin = int(w.shape[0]), int(w.shape[1])
+        coutp, cinp = pad8(cout), pad8(cin)
+        pad_ci, pad_co = (cinp + 63) // 64 * 64, (coutp + 63) // 64 * 64
+        assert ws.dtype == w.dtype == buf.dtype == torch.float32 and w.is_contiguous() and buf.is_contiguous() and ws.numel() == 9 * coutp * cinp
+        assert fwd is None or (fwd.dtype == torch.bfloat16 and fwd.numel() == 9 * coutp * pad_ci)
+        assert dgr is None or (dgr.dtype == torch.bfloat16 and dgr.numel() == 9 * cinp * pad_co)
+        tab[i] = (ws.data_ptr(), 0 if dw is None else dw.data_ptr(), w.data_ptr(), buf.data_ptr(), 0 if b is None else b.data_ptr(),
+                  0 if fwd is None else fwd.data_ptr(), 0 if dgr is None else dgr.data_ptr(), 0 if bo is None else bo.data_ptr(),
+                  cout, cin, coutp, cinp, L.lib().fosvos_conv3x3_wgrad_tc_orientation(cinp, coutp), pad_ci, pad_co, 0, lr, wd)
+        counts.append(L.lib().fosvos_repack_tile_count(cout, cin))
+    if out is not None:
+        t, prefix, n, tiles = out
+        new = torch.from_numpy(tab.view(np.uint8).copy())
+        if t.numel() == new.numel() and n == len(counts) and tiles == int(sum(counts)):
+            t.copy_(new)
+            return out
+    return _tile_table(tab, counts, device)
+
+
+def conv_step_all(table, momentum: float) -> None:
+    t, prefix, n, tiles = table
+    L.check(L.lib().fosvos_conv_step_all(t.data_ptr(), n, prefix.data_ptr(), tiles, float(momentum), L.stream()), "conv_step_all")
+
+
 def repack_all(table) -> None:
     t, prefix, n, tiles = table
     L.check(L.lib().fosvos_repack_all(t.data_ptr(), n, prefix.data_ptr(), tiles, L.stream()), "repack_all")

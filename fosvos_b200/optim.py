@@ -33,12 +33,32 @@ class FusedSGD(Optimizer):
         self._table = None
         self._table_key = None
         self._table_gen = 0          # bumps when the device table is REPLACED (captured graphs holding its address go stale)
+        self._exclude = set()        # ids of parameters stepped elsewhere (the trainer's fused conv-weight step)
+
+    def exclude(self, params) -> None:
+        """Leave these parameters to another kernel (``OnlineTrainer``'s fused fold + SGD + repack of the conv weights); their
+        momentum buffers still live in ``self.state`` so ``state_dict()`` keeps the torch.optim.SGD layout."""
+        self._exclude = {id(p) for p in params}
+        self._table_key = None
+
+    def group_options(self, p):
+        """(lr, weight_decay) of the group holding parameter ``p``."""
+        for g in self.param_groups:
+            if any(q is p for q in g["params"]):
+                return float(g["lr"]), float(g["weight_decay"])
+        raise KeyError("parameter is in no param group")
+
+    def momentum_buffer(self, p) -> torch.Tensor:
+        st = self.state[p]
+        if "momentum_buffer" not in st or st["momentum_buffer"] is None:
+            st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        return st["momentum_buffer"]
 
     def _entries(self):
         ent = []
         for g in self.param_groups:
             for p in g["params"]:
-                if p.grad is None:
+                if p.grad is None or id(p) in self._exclude:
                     continue
                 st = self.state[p]
                 if "momentum_buffer" not in st or st["momentum_buffer"] is None:

@@ -330,6 +330,24 @@ typedef struct fosvos_repack_entry {
   int Cout, Cin;
   int pad_ci, pad_co;  /* K extents of the two packed layouts: ceil64(CinP), ceil64(CoutP) */
 } fosvos_repack_entry;
+/* fold + SGD + repack of the 3x3 conv weights fused into ONE launch (the single-GPU fine-tune step):
+ * g = ws (+ dw if non-NULL; both cleared);  buf = momentum*buf + (g + weight_decay*w);  w -= lr*buf;  packed copies and
+ * padded bias rebuilt from the new w (bias itself is stepped by fosvos_sgd_step before).  Tiles as fosvos_repack_tile_count. */
+typedef struct fosvos_convstep_entry {
+  float* ws;           /* [tap][M][N] accumulator of fosvos_conv3x3_wgrad_tc_accumulate */
+  float* dw;           /* OIHW .grad or NULL */
+  float* w;            /* (Cout,Cin,3,3) fp32 parameter */
+  float* buf;          /* momentum buffer, same shape */
+  const float* bias;   /* Cout fp32 or NULL */
+  void* out_fwd;       /* FOSVOS_W_TC_FWD bf16 or NULL */
+  void* out_dgrad;     /* FOSVOS_W_TC_DGRAD bf16 or NULL */
+  float* bias_out;     /* CoutP fp32 or NULL */
+  int Cout, Cin, CoutP, CinP;
+  int x_is_a, pad_ci, pad_co, pad_;
+  float lr, weight_decay;
+} fosvos_convstep_entry;
+int fosvos_conv_step_all(const fosvos_convstep_entry* table, int n_entries, const int* tile_prefix, int n_tiles,
+                         float momentum, fosvos_stream_t stream);
 int fosvos_conv3x3_wgrad_tc_orientation(int CinP, int CoutP);
 int fosvos_fold_tile_count(int Cout, int Cin);
 int fosvos_repack_tile_count(int Cout, int Cin);

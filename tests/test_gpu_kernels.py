@@ -367,6 +367,51 @@ def test_conv3x3_wgrad_tc_accumulate_finish(case, splits, monkeypatch):
     assert float(ws.abs().max()) == 0.0
 
 
+def test_fused_conv_step_equals_fold_sgd_repack():
+    """`conv_step_all` (fold + SGD with momentum + repack of the 3x3 conv weights in one launch, step.cu) against the three
+    separate launches it replaces, two steps (the second with a momentum history), several shapes incl. ragged tiles."""
+    g = _gen(33)
+    shapes = [(64, 3), (16, 128), (72, 40), (128, 64), (64, 64)]
+    mu = 0.9
+    st = []
+    for k, (cout, cin) in enumerate(shapes):
+        cinp, coutp = ops.pad8(cin), ops.pad8(cout)
+        w = torch.randn(cout, cin, 3, 3, generator=g).to(DEV)
+        b = torch.randn(cout, generator=g).to(DEV)
+        st.append(dict(cout=cout, cin=cin, cinp=cinp, coutp=coutp, lr=1e-3 * (k + 1), wd=2e-4 if k % 2 == 0 else 0.0,
+                       w_a=w.clone(), w_b=w.clone(), buf_a=torch.zeros_like(w), buf_b=torch.zeros_like(w), bias=b,
+                       ws_a=ops.wgrad_workspace(cinp, coutp, DEV), ws_b=ops.wgrad_workspace(cinp, coutp, DEV),
+                       dw=torch.zeros_like(w),
+                       fwd_a=ops.pack_weight(w, L.W_TC_FWD, torch.bfloat16), dgr_a=ops.pack_weight(w, L.W_TC_DGRAD, torch.bfloat16),
+                       fwd_b=ops.pack_weight(w, L.W_TC_FWD, torch.bfloat16), dgr_b=ops.pack_weight(w, L.W_TC_DGRAD, torch.bfloat16),
+                       bo_a=ops.pad_bias(None, cout, DEV), bo_b=ops.pad_bias(None, cout, DEV)))
+    fold_t = ops.fold_table([(e["ws_a"], e["dw"]) for e in st], DEV)
+    sgd_t = ops.sgd_table([(e["w_a"], e["dw"], e["buf_a"], e["lr"], e["wd"]) for e in st], DEV)
+    rep_t = ops.repack_table([(e["w_a"], e["bias"], e["fwd_a"], e["dgr_a"], e["bo_a"]) for e in st], DEV)
+    conv_t = ops.convstep_table([(e["ws_b"], None, e["w_b"], e["buf_b"], e["bias"], e["fwd_b"], e["dgr_b"], e["bo_b"], e["lr"], e["wd"]) for e in st], DEV)
+    for step in range(2):
+        for e in st:
+            x = _nhwc(_bf16r(torch.randn(1, e["cin"], 10, 16, generator=g)), torch.bfloat16)
+            dz = _nhwc(_bf16r(torch.randn(1, e["cout"], 10, 16, generator=g)), torch.bfloat16)
+            ops.conv3x3_wgrad_accumulate(x, dz, e["ws_a"], None, e["cout"])
+            e["ws_b"].copy_(e["ws_a"])
+        ops.wgrad_fold_all(fold_t)
+        ops.sgd_step(sgd_t[0], sgd_t[1], len(st), sgd_t[2], mu, True)
+        ops.repack_all(rep_t)
+        ops.conv_step_all(conv_t, mu)
+        for e in st:
+            assert float(e["ws_b"].abs().max()) == 0.0
+            assert torch.allclose(e["w_b"], e["w_a"], rtol=1e-6, atol=1e-7), (step, float((e["w_b"] - e["w_a"]).abs().max()))
+            assert torch.allclose(e["buf_b"], e["buf_a"], rtol=1e-6, atol=1e-7)
+            assert torch.equal(e["bo_b"], e["bo_a"])
+            # the packed copies are bf16 roundings of (nearly) identical fp32 weights
+            assert float((e["fwd_b"].float() - e["fwd_a"].float()).abs().max()) <= 2 ** -7 * float(e["w_a"].abs().max())
+            assert float((e["dgr_b"].float() - e["dgr_a"].float()).abs().max()) <= 2 ** -7 * float(e["w_a"].abs().max())
+    # in-place rewrite of the table (new learning rates) keeps its device buffer
+    conv_t2 = ops.convstep_table([(e["ws_b"], None, e["w_b"], e["buf_b"], e["bias"], e["fwd_b"], e["dgr_b"], e["bo_b"], 2 * e["lr"], e["wd"]) for e in st], DEV, out=conv_t)
+    assert conv_t2[0].data_ptr() == conv_t[0].data_ptr()
+
+
 def test_multi_tensor_fold_and_repack():
     """One-launch `wgrad_fold_all` / `repack_all` over several convs == the per-layer finish / pack calls."""
     g = _gen(31)
