@@ -564,15 +564,24 @@ def test_step_graph_follows_param_group_changes():
         tr = OnlineTrainer(net, fix["H"], fix["W"], 2, opt, use_graph=use_graph)
         tr.set_frame(x.to(DEV), m.to(DEV))
         tr.run(2)
+        first = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
         for grp in opt.param_groups:
             grp["lr"] *= 3.0
         opt.param_groups[0]["weight_decay"] = 0.01
         tr.run(2)
-        res.append({k: v.detach().cpu().clone() for k, v in net.state_dict().items()})
+        res.append((first, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}))
     for k in ["stages.0.0.weight", "stages.3.3.weight", "side_prep.0.bias", "fuse.weight"]:
-        d0, d1 = res[0][k] - sd[k], res[1][k] - sd[k]
-        assert float(d0.abs().max()) > 0
-        assert float((d0 - d1).abs().max()) <= 1e-3 * float(d0.abs().max()) + 1e-12, k
+        for stage in (0, 1):                                   # after the first step, after the second (new lr / wd)
+            d0, d1 = res[0][stage][k] - sd[k], res[1][stage][k] - sd[k]
+            assert float(d0.abs().max()) > 0
+            err = float((d0 - d1).abs().max())
+            print(k, "step", stage + 1, "eager-vs-graph max diff", err, "of", float(d0.abs().max()))
+            # (fp32 direct weight gradients sum with atomics: the two trainers differ by summation order only)
+            assert err <= 2e-3 * float(d0.abs().max()) + 1e-9, (k, stage)
+    # the change of lr must show: the second update is ~3x the first (momentum adds to it)
+    k = "stages.3.3.weight"
+    s1 = float((res[1][0][k] - sd[k]).abs().max()); s2 = float((res[1][1][k] - res[1][0][k]).abs().max())
+    assert s2 > 2.0 * s1, (s1, s2)
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32_tc", 1e-4), ("bf16x3", None)])
