@@ -803,6 +803,10 @@ def config5_leg(args, rank, world, dev, sd0, frames_d, masks_d, windows=6):
     from fosvos_b200.online import OnlineTrainer
     n_local = args.avg_grad_every_n
     res = {}
+    # same optimizer-step kernels in all three schedules (the single-GPU trainer would otherwise fuse fold + SGD + repack, which
+    # the data-parallel ones cannot: the all-reduce sits between the fold and the SGD step)
+    fused_step_env = os.environ.get("FOSVOS_FUSED_STEP")
+    os.environ["FOSVOS_FUSED_STEP"] = "0"
     for name, dp, overlap in (("no_exchange", False, False), ("flat_allreduce", True, False), ("bucketed_overlapped", True, True)):
         net = FB.OSVOS_VGG(pretrained=0)
         net.load_state_dict(sd0)
@@ -824,6 +828,10 @@ def config5_leg(args, rank, world, dev, sd0, frames_d, masks_d, windows=6):
                 res[name]["capture_error"] = tr.overlap_capture_error
         del tr, net
         torch.cuda.empty_cache()
+    if fused_step_env is None:
+        os.environ.pop("FOSVOS_FUSED_STEP", None)
+    else:
+        os.environ["FOSVOS_FUSED_STEP"] = fused_step_env
     base = res["no_exchange"]["ms_per_optimizer_step"]
     for k in ("flat_allreduce", "bucketed_overlapped"):
         res[k]["exposed_allreduce_ms"] = res[k]["ms_per_optimizer_step"] - base

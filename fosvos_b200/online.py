@@ -119,7 +119,7 @@ class OnlineTrainer:
     def __init__(self, net: OSVOS_VGG, height: int, width: int, avg_grad_every_n: int = 5,
                  optimizer: Optional[FusedSGD] = None, use_graph: bool = True, deep_supervision: Optional[float] = None,
                  data_parallel: bool = False, world_size: int = 1, fuse_window: bool = True,
-                 share_with: Optional["OnlineTrainer"] = None, overlap_allreduce: bool = True):
+                 share_with: Optional["OnlineTrainer"] = None, overlap_allreduce: bool = False):
         self.device = next(net.parameters()).device
         with torch.cuda.device(self.device):
             self._init(net, height, width, avg_grad_every_n, optimizer, use_graph, deep_supervision, data_parallel, world_size,
@@ -135,7 +135,8 @@ class OnlineTrainer:
         ``data_parallel``: offline parent training sharded over ``world_size`` ranks (one process per GPU): every
         rank runs ``avg_grad_every_n // world_size`` micro-iterations on its own frames, gradients (scaled by
         1/avg_grad_every_n as in the reference) are summed with ONE all-reduce of a flat fp32 buffer, then every
-        rank applies the same optimizer step.  With ``overlap_allreduce`` the flat buffer is laid out in per-stage buckets
+        rank applies the same optimizer step.  With ``overlap_allreduce`` (off by default: measured slower at 2 GPUs -- the NCCL
+        kernels take SMs from the persistent 148-CTA conv grids) the flat buffer is laid out in per-stage buckets
         (deepest stage first, the order the backward pass finishes them) and every bucket's weight-gradient fold +
         all-reduce is issued on a side stream as soon as that stage's weight gradients are done, so the exchange hides
         behind the rest of the backward pass (needs the fused window, runs it outside CUDA graphs).
