@@ -131,33 +131,68 @@ conv_step_kernel(const fosvos_convstep_entry* __restrict__ table, int n_entries,
     const int co0 = (local / ci_tiles) * PACK_CO, ci0 = (local % ci_tiles) * PACK_CI;
     const int nco = min(PACK_CO, e.Cout - co0), nci = min(PACK_CI, e.Cin - ci0);
     const long long plane = (long long)e.CoutP * e.CinP;
-    // 1. gather the accumulator tile (fastest index = the workspace's contiguous dimension) and clear it
-    for (int i = threadIdx.x; i < 9 * PACK_CO * PACK_CI; i += 256) {
-      int tap, co_l, ci_l;
-      if (e.x_is_a) { co_l = i % PACK_CO; ci_l = (i / PACK_CO) % PACK_CI; tap = i / (PACK_CO * PACK_CI); }
-      else          { ci_l = i % PACK_CI; co_l = (i / PACK_CI) % PACK_CO; tap = i / (PACK_CO * PACK_CI); }
-      if (co_l < nco && ci_l < nci) {
+    // 1. gather the accumulator tile (fastest index = the workspace's contiguous dimension) and clear it.  Loads are issued
+    // in batches of six BEFORE the stores that clear them: the compiler cannot move a load across an earlier store to the
+    // same array, and one load in flight per thread left the kernel latency-bound (2.4 TB/s)
+    constexpr int GB = 6;
+    static_assert((9 * PACK_CO * PACK_CI) % (256 * GB) == 0, "gather batches");
+    for (int i0 = threadIdx.x; i0 < 9 * PACK_CO * PACK_CI; i0 += 256 * GB) {
+      float v[GB];
+      float* src[GB];
+      int dst[GB];
+#pragma unroll
+      for (int u = 0; u < GB; ++u) {
+        const int i = i0 + 256 * u;
+        int tap, co_l, ci_l;
+        if (e.x_is_a) { co_l = i % PACK_CO; ci_l = (i / PACK_CO) % PACK_CI; tap = i / (PACK_CO * PACK_CI); }
+        else          { ci_l = i % PACK_CI; co_l = (i / PACK_CI) % PACK_CO; tap = i / (PACK_CO * PACK_CI); }
+        const bool ok = co_l < nco && ci_l < nci;
         const int co = co0 + co_l, ci = ci0 + ci_l;
-        float* src = e.ws + tap * plane + (e.x_is_a ? ((long long)ci * e.CoutP + co) : ((long long)co * e.CinP + ci));
-        sm[co_l * PITCH + ci_l * 9 + tap] = *src;
-        *src = 0.f;
+        src[u] = ok ? e.ws + tap * plane + (e.x_is_a ? ((long long)ci * e.CoutP + co) : ((long long)co * e.CinP + ci)) : nullptr;
+        dst[u] = co_l * PITCH + ci_l * 9 + tap;
+        v[u] = ok ? *src[u] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < GB; ++u) {
+        if (src[u]) {
+          sm[dst[u]] = v[u];
+          *src[u] = 0.f;
+        }
       }
     }
     __syncthreads();
-    // 2. SGD with momentum over the OIHW runs (nci * 9 contiguous floats per cout); the new weights replace the gradient in smem
-    const int run = nci * 9;
+    // 2. SGD with momentum over the OIHW runs (nci * 9 contiguous floats per cout); the new weights replace the gradient in
+    // smem.  Same batching: four elements' loads before their stores
+    const int run = nci * 9, total = nco * run;
     const float lr = e.lr, wd = e.weight_decay;
-    for (int i = threadIdx.x; i < nco * run; i += 256) {
-      const int co_l = i / run, r = i - co_l * run;
-      const long long gi = ((long long)(co0 + co_l) * e.Cin + ci0) * 9 + r;
-      float gv = sm[co_l * PITCH + r];
-      if (e.dw) { gv += e.dw[gi]; e.dw[gi] = 0.f; }
-      float pv = e.w[gi];
-      const float bv = mu * e.buf[gi] + (gv + wd * pv);
-      e.buf[gi] = bv;
-      pv -= lr * bv;
-      e.w[gi] = pv;
-      sm[co_l * PITCH + r] = pv;
+    constexpr int SB = 4;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 256 * SB) {
+      float pv[SB], bv[SB], dv[SB];
+      long long gi[SB];
+      int si[SB];
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        const int i = i0 + 256 * u;
+        const bool ok = i < total;
+        const int co_l = ok ? i / run : 0, r = ok ? i - co_l * run : 0;
+        gi[u] = ok ? ((long long)(co0 + co_l) * e.Cin + ci0) * 9 + r : -1;
+        si[u] = co_l * PITCH + r;
+        pv[u] = ok ? e.w[gi[u]] : 0.f;
+        bv[u] = ok ? e.buf[gi[u]] : 0.f;
+        dv[u] = (ok && e.dw) ? e.dw[gi[u]] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        if (gi[u] >= 0) {
+          const float gv = sm[si[u]] + dv[u];
+          const float b = mu * bv[u] + (gv + wd * pv[u]);
+          const float pn = pv[u] - lr * b;
+          e.buf[gi[u]] = b;
+          e.w[gi[u]] = pn;
+          if (e.dw) e.dw[gi[u]] = 0.f;
+          sm[si[u]] = pn;
+        }
+      }
     }
     if (ci0 == 0 && e.bias_out && threadIdx.x < nco)
       e.bias_out[co0 + threadIdx.x] = e.bias ? e.bias[co0 + threadIdx.x] : 0.f;

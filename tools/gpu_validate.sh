@@ -1,26 +1,22 @@
 #!/bin/bash
 # Round validation on one B200: parity tests, smoke, bench (both arms), ncu launch lists and --set full captures.
-# Outputs land in gpurun_out/ under the tag given as $1 (default r01i); summarise them into profiles/ with tools/ncu_summary.py.
-TAG=${1:-r01i}
+# Outputs land in gpurun_out/ under the tag given as $1; summarise them into profiles/ with tools/ncu_summary.py / conv_traffic.py.
+cd "$(dirname "$0")/.."
+TAG=${1:-r02k}
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -q -m gpu --timeout 150 -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|^E  +(Assert|assert|Runtime)|^FAILED" gpurun_out/t_all.log | cut -c1-300 | head
+timeout 600 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|^FAILED" gpurun_out/t_all.log | cut -c1-300 | head
 timeout 200 python __graft_entry__.py smoke > gpurun_out/t_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/t_smoke.log
 timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_$TAG.err
-python - <<PY
-import json
-d=json.load(open('gpurun_out/bench_$TAG.json'))
-print({k:d[k] for k in ('value','ms_per_step','inference_fps','finetune_s_per_sequence','finetune_tflops','gpu_launches')}, d['e2e'], d['roofline']['frac'], d['roofline_side_chain']['frac'], d['roofline_side_chain']['ms'], d['roofline_loss']['frac'], d['cpu_baseline']['value'], d['clocks'])
-PY
 timeout 300 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 timeout 120 python tools/profile_step.py 3 8 ft > gpurun_out/plain.log 2>&1 &&
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_ft_$TAG.csv python tools/profile_step.py 3 8 ft > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches ft rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_inf_$TAG.csv python tools/profile_step.py 3 16 inf > gpurun_out/ncu_launches2.log 2>&1
 echo "ncu launches inf rc=$?"
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tc_kernel" -s 34 -c 17 -o gpurun_out/prof_conv_$TAG -f python tools/profile_step.py 3 16 inf > gpurun_out/ncu_full1.log 2>&1
+timeout 700 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tc_kernel|conv3x3_side_tc_kernel" -s 34 -c 17 -o gpurun_out/prof_conv_$TAG -f python tools/profile_step.py 3 16 inf > gpurun_out/ncu_full1.log 2>&1
 echo "ncu full conv rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"wgrad_tc_kernel|side_upsample|side_heads|bal_loss_fused|maxpool_bwd|side_bwd" -s 17 -c 24 -o gpurun_out/prof_misc_$TAG -f python tools/profile_step.py 2 8 both > gpurun_out/ncu_full2.log 2>&1
-echo "ncu full misc rc=$?"
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"side_upsample_sep2|side_heads2" -s 4 -c 2 -o gpurun_out/prof_side_$TAG -f python tools/side_sep_probe.py 16 > gpurun_out/ncu_side.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"wgrad_tc_kernel|conv_step_kernel|side_bwd|maxpool_bwd" -s 17 -c 24 -o gpurun_out/prof_bwd_$TAG -f python tools/profile_step.py 2 8 ft > gpurun_out/ncu_full2.log 2>&1
+echo "ncu full bwd rc=$?"
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"side_upsample_sep2" -s 4 -c 1 -o gpurun_out/prof_side_$TAG -f python tools/side_sep_probe.py 16 > gpurun_out/ncu_side.log 2>&1
 echo "ncu full side rc=$?"
 timeout 100 python tools/side_sep_probe.py 1 5 16 2>&1 | tail -1
