@@ -24,9 +24,17 @@
 // LBO = 160 (next image row = next 8 pixels along K) one MMA covers the three taps of a kernel row (N = 32, the
 // fourth block is ignored), so a patch is visited once (not once per kernel column) and dZ is read once.
 //
-// Cin = 64 (`pair`): a 64-channel operand fills only half of the M = 128 rows.  With X on M the two halves of A are
-// the SAME 64 channels under two horizontal shifts (two halo boxes, LBO apart): rows 0..63 accumulate kernel column
-// s, rows 64..127 column s + 1 -- two kernel columns per pass, so the nine taps take two passes instead of three.
+// Row stack (`stack`, N tile of 64 channels with X on N: conv2_1): the three vertical taps of the X halo box are three
+// 64-column blocks of ONE N = 192 MMA -- an MN-major operand's 64-element blocks may sit anywhere LBO bytes apart, and
+// LBO = one image row of the patch makes block r the box seen through kernel row r.  A narrow MMA costs ~47 + N/4 cycles
+// whatever it computes (tools/exp/mma_major.cu: 71 / 79 / 128 cycles for N = 64 / 128 / 256), so one N = 192 MMA
+// (~96 cycles) replaces three N = 64 ones (213).
+//
+// Cin = Cout = 64 (`one_pass`, conv1_2): the same stack with the vertical shift moved to dZ -- sum_p dZ[p] X[p + (dy, dx)]
+// = sum_q dZ[q - (dy, 0)] X[q + (0, dx)] -- so B = dZ halo box (three row shifts, N = 192) and A = X under two horizontal
+// shifts (two plain boxes LBO apart, M = 128).  Two MMAs per 16 pixels -- kernel columns (0, 1) and (2, ignored rows) --
+// cover all nine taps from ONE visit of the patch (3 X boxes + 1 dZ halo box = 68 KB), instead of six N = 64 MMAs in
+// each of two passes over both operands.
 //
 // Bias gradient db[co] = sum_p dZ[p][co]: the dZ boxes are in shared memory anyway, so the four epilogue
 // warps, otherwise idle until the accumulators are complete, sum them on the side; the CTAs that see the
@@ -58,9 +66,10 @@ struct WgParams {
   int stages, stage_bytes, a_bytes;
   int x_block;               // bytes of one shifted 64-channel box: (TH+2)*TW*128
   int c8;                    // first-layer mode (see the header comment)
-  int pair;                  // Cin == 64: the two 64-row halves of A are two kernel columns of the same channels
+  int stack;                 // N = 64 tile, X on N: the three kernel rows are one N = 192 MMA (LBO = one image row of the patch)
+  int one_pass;              // Cin == Cout == 64: A = X under two column shifts, B = dZ under three row shifts, all taps per visit
   int c8_lbo, c8_sbo;        // descriptor strides of its un-swizzled X operand (160 / 16)
-  int debug;                 // FOSVOS_WG_DEBUG: 1 = skip the reductions (timing experiments only), 2 = no start rotation
+  int debug;                 // FOSVOS_WG_DEBUG (timing experiments only): 1 = skip the reductions, 2 = no start rotation, 3 = no MMAs, 4 = no loads, 5 = neither, 6 = 5 + 1
 };
 
 // MN-major SWIZZLE_128B operand: rows (K) of 128 B, 8-row groups SBO = 1024 B apart, 64-element
@@ -105,8 +114,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   // work item
   int item = blockIdx.x;
   const int split = item % p.splits; item /= p.splits;
-  const int n_s = p.c8 ? 1 : p.pair ? 2 : 3;        // passes over the kernel columns
-  const int s = p.pair ? 2 * (item % n_s) : item % n_s;   // (first) kernel column of this pass
+  const int n_s = (p.c8 || p.one_pass) ? 1 : 3;     // passes over the kernel columns
+  const int s = item % n_s;                         // kernel column of this pass
   item /= n_s;
   const int nt = item % p.n_tiles;
   const int mt = item / p.n_tiles;
@@ -115,7 +124,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   // slowing one CTA in three -- the MMA stream already uses the full shared-memory bandwidth.
   const bool do_bias = p.db != nullptr;
   const int share = n_s * (p.x_is_a ? p.m_tiles : p.n_tiles);
-  const int share_id = (p.pair ? s / 2 : s) * (p.x_is_a ? p.m_tiles : p.n_tiles) + (p.x_is_a ? mt : nt);
+  const int share_id = s * (p.x_is_a ? p.m_tiles : p.n_tiles) + (p.x_is_a ? mt : nt);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform roles
   if (warp == 0 && lane == 0) {
@@ -151,7 +160,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const int nb_x = p.x_is_a ? 2 : p.nb_n;
   const int nb_z = p.x_is_a ? p.nb_n : 2;
   const int x_off = p.x_is_a ? 0 : p.a_bytes;  // byte offset of the X boxes inside a stage
-  const int z_off = p.x_is_a ? p.a_bytes : 0;
+  const int z_off = p.one_pass ? p.a_bytes + TW * 128 : p.x_is_a ? p.a_bytes : 0;   // (one_pass: the patch inside the dZ halo box)
 
   if (warp == 0) {
     {
@@ -172,14 +181,19 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             for (int j = 0; j < nb_z; ++j)
               ptx::tma_load_4d(st + z_off + j * WG_PLAIN_BLOCK, &map_z, &full_bar[stage], zc0 + 64 * j, x0, y0, n);
           }
+        } else if (p.debug >= 4) {              // timing experiment: no loads
+          if (ptx::elect_one()) ptx::mbar_arrive(&full_bar[stage]);
+        } else if (p.one_pass) {
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+            for (int j = 0; j < 3; ++j)          // X through kernel column j (plain boxes), then the dZ halo box
+              ptx::tma_load_4d(st + j * WG_PLAIN_BLOCK, &map_x, &full_bar[stage], 0, x0 + j - 1, y0, n);
+            ptx::tma_load_4d(st + p.a_bytes, &map_z, &full_bar[stage], 0, x0, y0 - 1, n);
+          }
         } else if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
-          for (int j = 0; j < nb_x; ++j) {
-            // pair mode: box j = the same channels one kernel column further (the last pass repeats column 2: ignored rows)
-            const int cj = p.pair ? xc0 : xc0 + 64 * j;
-            const int sj = p.pair ? min(s + j, 2) : s;
-            ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], cj, x0 + sj - 1, y0 - 1, n);
-          }
+          for (int j = 0; j < nb_x; ++j)
+            ptx::tma_load_4d(st + x_off + j * p.x_block, &map_x, &full_bar[stage], xc0 + 64 * j, x0 + s - 1, y0 - 1, n);
           for (int j = 0; j < nb_z; ++j)
             ptx::tma_load_4d(st + z_off + j * WG_PLAIN_BLOCK, &map_z, &full_bar[stage], zc0 + 64 * j, x0, y0, n);
         }
@@ -192,7 +206,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       // kind::f16, D fp32, A/B bf16, both MN-major (bits 15/16), M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t lbo_a = p.x_is_a ? p.x_block : WG_PLAIN_BLOCK;
+      const uint32_t lbo_a = (p.x_is_a && !p.one_pass) ? p.x_block : WG_PLAIN_BLOCK;
       const uint32_t lbo_b = p.x_is_a ? WG_PLAIN_BLOCK : p.x_block;
       const uint32_t tap_bytes = (uint32_t)TW * 128;       // one image row of the patch
       int stage = 0;
@@ -217,9 +231,26 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             ptx::umma_commit(&empty_bar[stage]);
             if (pt == p_end - 1) ptx::umma_commit(done_bar);
           }
+        } else if (p.one_pass || p.stack) {
+          if (ptx::elect_one()) {
+            const uint32_t idesc192 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(192 >> 3) << 17);
+            if (p.debug != 3 && p.debug < 5) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                // B: three 64-column blocks one image row of the patch apart = the box through kernel rows 0..2
+                const uint64_t db = umma_desc_sw128_mnmajor(b_base + kk * 2048, tap_bytes);
+                const uint32_t acc = (pt != p_begin) || (kk != 0);
+                ptx::umma_bf16(tmem_base, umma_desc_sw128_mnmajor(a_base + kk * 2048, lbo_a), db, idesc192, acc);
+                // one_pass: rows 0..63 = kernel column 2, rows 64..127 read the head of the dZ box (never stored)
+                if (p.one_pass) ptx::umma_bf16(tmem_base + 192, umma_desc_sw128_mnmajor(a_base + 2 * WG_PLAIN_BLOCK + kk * 2048, lbo_a), db, idesc192, acc);
+              }
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (pt == p_end - 1) ptx::umma_commit(done_bar);
+          }
         } else if (ptx::elect_one()) {
 #pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < ((p.debug == 3 || p.debug >= 5) ? 0 : 3); ++r) {        // debug 3: timing experiment without the MMAs
           const uint32_t a_r = a_base + (p.x_is_a ? r * tap_bytes : 0);
           const uint32_t b_r = b_base + (p.x_is_a ? 0 : r * tap_bytes);
 #pragma unroll
@@ -282,9 +313,9 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         for (int e = 0; e < 8; ++e) atomicAdd(&bias_red[b * 64 + c * 8 + e], acc[b][e]);
     }
     if (p_end > p_begin) {
-      ptx::mbar_wait(done_bar, 0);
+      ptx::mbar_wait_idle(done_bar, 0);
       ptx::tc_fence_after();
-      const bool row_ok = (p.pair ? (s + (row >> 6)) < 3 : (m0 + row) < p.Mtot) && p.debug != 1;
+      const bool row_ok = (m0 + row) < p.Mtot && p.debug != 1 && p.debug != 6;
       // the splits of one tile finish together and add into the same addresses: start each at a different
       // (kernel row, column block) so that concurrent reductions mostly hit different L2 lines
       const int rot = p.debug == 2 ? 0 : split;
@@ -312,11 +343,33 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
           }
         }
+      } else if (p.one_pass) {
+        // accumulator a (0: kernel columns 0 / 1 on rows 0..63 / 64..127; 1: column 2 on rows 0..63), column block i = the dZ
+        // box shifted down by i rows = kernel row 2 - i: ws[tap][cin][cout]
+        for (int ai = 0; ai < 6; ++ai) {
+          const int a = ((ai + rot) % 6) / 3, i = (ai + rot) % 3;
+          const int sj = a ? 2 : (row >> 6);
+          const bool ok = p.debug != 1 && p.debug != 6 && (a == 0 || row < 64);
+          float* dst = p.ws + ((long long)((2 - i) * 3 + sj) * p.Mtot + (row & 63)) * p.Ntot;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + a * 192 + i * 64;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld16(taddr + c0, v);
+            ptx::tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                red_add_v4(dst + c0 + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                           __uint_as_float(v[4 * q + 3]));
+            }
+          }
+        }
       } else
       for (int rr = 0; rr < 3; ++rr) {
         const int r = (rr + rot) % 3;
-        const int tap = r * 3 + s + (p.pair ? (row >> 6) : 0);
-        const int mrow = p.pair ? (row & 63) : m0 + row;
+        const int tap = r * 3 + s;
+        const int mrow = m0 + row;
         float* dst = p.ws + ((long long)tap * p.Mtot + mrow) * p.Ntot + n0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * p.n_cols;
 #pragma unroll 1
@@ -348,6 +401,210 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2) for the wide layers: Cout % 256 == 0, Cin % 128 == 0, dZ on M.
+//
+// A single-CTA M = 128, N = 128 MMA is exactly operand-read balanced (A 4 KB + B 4 KB at 128 B/clk = 64 cycles for 64
+// cycles of tensor work), so every stall shows, and each CTA pulls 72 KB per 128-pixel patch through L2.  A pair of CTAs
+// on the two SMs of a TPC runs ONE M = 256 x N = 128 MMA per step: each SM reads its own 128 dZ channels (A) and only
+// HALF of the X tile (64 of the 128 cin channels; the tensor cores exchange the halves), 48 operand cycles under 64 tensor
+// cycles, and 52 KB per patch and CTA through L2.  Work item = (256-cout tile, 128-cin tile, kernel column s, pixel
+// range); the three accumulators (kernel rows) are 128 columns each in BOTH CTAs' TMEM (rows 0..127 / 128..255 of the
+// cout tile).  Both CTAs run a TMA producer for their own halves; all bytes of a stage are counted on CTA 0's `full`
+// barrier, where the one MMA-issuing thread of the pair waits; its commits arrive on both CTAs' `empty` / `done`
+// barriers (multicast).  CTA 1's bias-summing warps learn that a stage has landed from a remote arrive on `landed`.
+struct WgPairParams {
+  float* ws;                 // [9][CoutP][CinP] fp32
+  float* db;
+  int cout;
+  int CoutP, CinP;
+  int n_tiles, splits;       // 128-cin tiles; pixel-range splits
+  int tiles_x, tiles_y, patches;
+  int tw_shift;
+  int stages, stage_bytes, x_block;
+  int debug;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
+conv3x3_wgrad_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z, const WgPairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // both CTAs must lay their shared memory out identically: the MMA descriptors and the multicast commits address by offset
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* landed_bar = empty_bar + p.stages;
+  uint64_t* done_bar = landed_bar + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+  __shared__ float bias_red[128];
+
+  const uint32_t rank = ptx::cluster_ctarank();
+  int item = blockIdx.x >> 1;
+  const int split = item % p.splits; item /= p.splits;
+  const int s = item % 3; item /= 3;
+  const int nt = item % p.n_tiles;
+  const int mt = item / p.n_tiles;
+  const bool do_bias = p.db != nullptr;
+  const int share = 3 * p.n_tiles;                 // CTAs that see this CTA's dZ half-tile
+  const int share_id = s * p.n_tiles + nt;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_z);
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);                      // CTA 0's producer (expect_tx for both CTAs' bytes)
+      ptx::mbar_init(&empty_bar[i], do_bias ? 5 : 1);       // the pair's MMA commit (+ this CTA's four bias-summing warps)
+      ptx::mbar_init(&landed_bar[i], 1);                    // CTA 1 only: remote arrive from CTA 0's MMA warp
+    }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 128) bias_red[threadIdx.x] = 0.f;
+  if (warp == 1) ptx::tmem_alloc_pair(tmem_ptr, 512);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                                      // barriers of both CTAs initialised before any remote traffic
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int p_begin = (int)((long long)p.patches * split / p.splits);
+  const int p_end = (int)((long long)p.patches * (split + 1) / p.splits);
+  const int TW = 1 << p.tw_shift, TH = 128 >> p.tw_shift;
+  const int zc0 = mt * 256 + (int)rank * 128;      // this CTA's dZ channels (its 128 rows of the M = 256 tile)
+  const int xc0 = nt * 128 + (int)rank * 64;       // this CTA's half of the X tile (64 of the N = 128 columns)
+  const int a_bytes = 2 * WG_PLAIN_BLOCK;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = p_begin; pt < p_end; ++pt) {
+      int t = pt;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int n = t / p.tiles_y;
+      const int x0 = tx * TW, y0 = ty * TH;
+      ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = smem + stage * p.stage_bytes;
+      if (ptx::elect_one()) {
+        const uint32_t lead = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+        if (p.debug >= 4) {                     // timing experiment: no loads, the MMAs run on whatever the stage holds
+          if (rank == 0) ptx::mbar_arrive(&full_bar[stage]);
+        } else {
+        if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
+        ptx::tma_load_4d_pair(st, &map_z, lead, zc0, x0, y0, n);
+        ptx::tma_load_4d_pair(st + WG_PLAIN_BLOCK, &map_z, lead, zc0 + 64, x0, y0, n);
+        ptx::tma_load_4d_pair(st + a_bytes, &map_x, lead, xc0, x0 + s - 1, y0 - 1, n);
+        }
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // kind::f16, D fp32, A/B bf16, both MN-major (bits 15/16), M = 256 over the pair, N = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t tap_bytes = (uint32_t)TW * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = p_begin; pt < p_end; ++pt) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t st = ptx::smem_u32(smem + stage * p.stage_bytes);
+        if (do_bias && lane == 31) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(ptx::smem_u32(&landed_bar[stage]), 1));
+        if (ptx::elect_one()) {
+#pragma unroll 1
+          for (int r = 0; r < ((p.debug == 3 || p.debug >= 5) ? 0 : 3); ++r) {      // debug 3: timing experiment without the MMAs
+            const uint32_t b_r = st + a_bytes + r * tap_bytes;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t da = umma_desc_sw128_mnmajor(st + kk * 2048, WG_PLAIN_BLOCK);
+              const uint64_t db = umma_desc_sw128_mnmajor(b_r + kk * 2048, p.x_block);
+              ptx::umma_bf16_pair(tmem_base + r * 128, da, db, idesc, (pt != p_begin) || (kk != 0));
+            }
+          }
+          ptx::umma_commit_pair(&empty_bar[stage], 3);
+          if (pt == p_end - 1) ptx::umma_commit_pair(done_bar, 3);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    if (do_bias) {
+      const int t = threadIdx.x - 64;
+      const int c = t & 7, rg = t >> 3;
+      const uint32_t off = (uint32_t)rg * 128 + (uint32_t)((c ^ (rg & 7)) << 4);
+      float acc[2][8];
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[b][e] = 0.f;
+      uint64_t* ready = rank == 0 ? full_bar : landed_bar;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = p_begin; pt < p_end; ++pt) {
+        ptx::mbar_wait(&ready[stage], phase);
+        const uint8_t* zb = smem + stage * p.stage_bytes + off;
+        if ((pt % share) == share_id) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 v = *reinterpret_cast<const uint4*>(zb + b * WG_PLAIN_BLOCK + j * 2048);
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                acc[b][2 * q] += __uint_as_float(w[q] << 16);
+                acc[b][2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&bias_red[b * 64 + c * 8 + e], acc[b][e]);
+    }
+    ptx::mbar_wait_idle(done_bar, 0);
+    ptx::tc_fence_after();
+    const int rot = p.debug == 2 ? 0 : split;
+    for (int rr = 0; rr < 3; ++rr) {
+      const int r = (rr + rot) % 3;
+      float* dst = p.ws + ((long long)(r * 3 + s) * p.CoutP + zc0 + row) * p.CinP + nt * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * 128;
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        const int c0 = ((cb + rot / 3) & 7) << 4;
+        uint32_t v[16];
+        ptx::tmem_ld16(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        if (p.debug != 1 && p.debug != 6) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            red_add_v4(dst + c0 + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                       __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+    if (do_bias) {
+      ptx::named_bar_sync(1, 128);
+      const int t = threadIdx.x - 64;
+      if (zc0 + t < p.cout) atomicAdd(p.db + zc0 + t, bias_red[t]);
+    }
+  }
+  // neither CTA may leave (or free TMEM) while the other's MMAs / commits / TMA signals can still touch it
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -448,10 +705,12 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   p.Mtot = p.x_is_a ? CinP : CoutP;
   p.Ntot = p.x_is_a ? CoutP : CinP;
   p.c8 = (CinP == 8 && !p.x_is_a && !getenv("FOSVOS_WG_NO_C8")) ? 1 : 0;
-  p.pair = (p.x_is_a && CinP == 64) ? 1 : 0;
+  static const bool no_stack = getenv("FOSVOS_WG_NO_STACK") != nullptr;      // A/B switch (timing experiments)
+  p.one_pass = (p.x_is_a && CinP == 64 && CoutP == 64 && !no_stack) ? 1 : 0;
   p.c8_lbo = WG_C8_ROW; p.c8_sbo = 16;
   p.n_cols = p.c8 ? 32 : p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
   p.nb_n = (p.n_cols + 63) / 64;
+  p.stack = (!p.x_is_a && !p.c8 && p.Ntot == 64 && !no_stack) ? 1 : 0;
   p.m_tiles = ceil_div(p.Mtot, 128);
   p.n_tiles = ceil_div(p.Ntot, p.n_cols);
   // 128-pixel patch with TW % 8 == 0 that wastes the fewest out-of-frame pixels
@@ -469,7 +728,8 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   p.patches = N * p.tiles_x * p.tiles_y;
   p.x_block = (TH + 2) * TW * 128;
   const int nb_x = p.x_is_a ? 2 : p.nb_n, nb_z = p.x_is_a ? p.nb_n : 2;
-  const int x_bytes = p.c8 ? WG_C8_BYTES : nb_x * p.x_block, z_bytes = nb_z * WG_PLAIN_BLOCK;
+  // one_pass: X as three plain boxes (kernel columns), dZ as ONE halo box (kernel rows)
+  const int x_bytes = p.c8 ? WG_C8_BYTES : p.one_pass ? 3 * WG_PLAIN_BLOCK : nb_x * p.x_block, z_bytes = p.one_pass ? p.x_block : nb_z * WG_PLAIN_BLOCK;
   p.a_bytes = p.x_is_a ? x_bytes : z_bytes;
   p.stage_bytes = x_bytes + z_bytes;
   p.stages = min(6, (220 * 1024 - 2048) / p.stage_bytes);
@@ -477,18 +737,48 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   // Split-K over pixel ranges.  Every CTA ends with 3 * 128 * n_cols fp32 reductions into the workspace, so the
   // split count trades tensor-core occupancy against reduction traffic: fill the machine once; go to a second
   // wave only while each CTA still has enough patches to amortise its epilogue.
-  const int items = p.m_tiles * p.n_tiles * (p.c8 ? 1 : p.pair ? 2 : 3);
+  const int items = p.m_tiles * p.n_tiles * ((p.c8 || p.one_pass) ? 1 : 3);
   int splits = max(1, num_sms() / items);
-  if ((long long)p.patches >= 16LL * 2 * num_sms() / items) splits = max(1, (2 * num_sms()) / items);
+  static const bool two_waves = getenv("FOSVOS_WG_TWO_WAVES") != nullptr;   // (measured slower: 881 -> 822 us over the window's layers)
+  if (two_waves && (long long)p.patches >= 16LL * 2 * num_sms() / items) splits = max(1, (2 * num_sms()) / items);
   if (const char* e = getenv("FOSVOS_WG_SPLITS")) { const int v = atoi(e); if (v > 0) splits = v; }
   splits = min(splits, p.patches);
   p.splits = splits;
   { const char* e = getenv("FOSVOS_WG_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
+  // wide layers: CTA-pair kernel (M = 256 over two SMs)
+  static const bool pair_off = getenv("FOSVOS_WG_NO_CTA_PAIR") != nullptr;
+  if (!pair_off && !p.x_is_a && !p.c8 && CoutP % 256 == 0 && CinP % 128 == 0) {
+    WgPairParams q;
+    q.ws = p.ws; q.db = db; q.cout = Cout; q.CoutP = CoutP; q.CinP = CinP;
+    q.n_tiles = CinP / 128;
+    q.tiles_x = p.tiles_x; q.tiles_y = p.tiles_y; q.patches = p.patches; q.tw_shift = p.tw_shift;
+    q.x_block = p.x_block;
+    q.stage_bytes = 2 * WG_PLAIN_BLOCK + p.x_block;
+    q.stages = min(6, (220 * 1024 - 2048) / q.stage_bytes);
+    q.debug = p.debug;
+    const int pair_items = (CoutP / 256) * q.n_tiles * 3;
+    int psplits = max(1, (num_sms() / 2) / pair_items);        // one wave of CTA pairs: one epilogue per SM
+    if (const char* e = getenv("FOSVOS_WG_SPLITS")) { const int v = atoi(e); if (v > 0) psplits = v; }
+    q.splits = min(psplits, p.patches);
+    CUtensorMap mx, mz;
+    int rc = wg_encode(&mx, x, N, H, W, CinP, TW, TH + 2);
+    if (rc) return rc;
+    rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, TH);
+    if (rc) return rc;
+    static unsigned long long pair_smem_set = 0;
+    if (first_use_on_device(pair_smem_set)) {
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e != cudaSuccess) { pair_smem_set = 0; set_error("cudaFuncSetAttribute(wgrad pair smem): %s", cudaGetErrorString(e)); return FOSVOS_ERR_LAUNCH; }
+    }
+    conv3x3_wgrad_tc_pair_kernel<<<2 * pair_items * q.splits, WG_THREADS, q.stages * q.stage_bytes + 1024 + 1024, st>>>(mx, mz, q);
+    return check_launch("conv3x3_wgrad_tc(pair)");
+  }
+
   CUtensorMap mx, mz;
-  int rc = p.c8 ? wg_encode_c8(&mx, x, N, H, W) : wg_encode(&mx, x, N, H, W, CinP, TW, TH + 2);
+  int rc = p.c8 ? wg_encode_c8(&mx, x, N, H, W) : wg_encode(&mx, x, N, H, W, CinP, TW, p.one_pass ? TH : TH + 2);
   if (rc) return rc;
-  rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, TH);
+  rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, p.one_pass ? TH + 2 : TH);
   if (rc) return rc;
 
   const int smem_bytes = p.stages * p.stage_bytes + 1024 + 1024;

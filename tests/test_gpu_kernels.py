@@ -320,9 +320,12 @@ def test_conv3x3_wgrad(dt, case):
 
 
 @pytest.mark.parametrize("case", [(1, 16, 24, 64, 64), (1, 17, 23, 64, 128), (2, 9, 30, 128, 16), (1, 33, 40, 256, 256),
-                                  (1, 30, 54, 512, 512), (1, 12, 20, 40, 72), (1, 8, 8, 128, 128)])
+                                  (1, 30, 54, 512, 512), (1, 12, 20, 40, 72), (1, 8, 8, 128, 128), (2, 17, 23, 128, 256),
+                                  (3, 20, 27, 256, 512), (2, 21, 37, 64, 64), (2, 13, 50, 64, 128), (1, 40, 40, 64, 256)])
 def test_conv3x3_wgrad_tc(case):
-    """tcgen05 weight gradient (MN-major operands, halo-box tap reuse, split-K reductions)."""
+    """tcgen05 weight gradient (MN-major operands, halo-box tap reuse, split-K reductions).  Cout % 256 == 0 with
+    Cin % 128 == 0 runs the CTA-pair kernel (cta_group::2, M = 256 over the two SMs of a TPC); Cin = 64 runs the row-stacked
+    N = 192 MMAs (Cout = 64: all nine taps from one visit of each patch)."""
     n, h, w_, cin, cout = case
     g = _gen(17)
     x = _bf16r(torch.randn(n, cin, h, w_, generator=g))
