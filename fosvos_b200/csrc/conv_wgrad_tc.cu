@@ -30,11 +30,15 @@
 // whatever it computes (tools/exp/mma_major.cu: 71 / 79 / 128 cycles for N = 64 / 128 / 256), so one N = 192 MMA
 // (~96 cycles) replaces three N = 64 ones (213).
 //
-// Cin = Cout = 64 (`one_pass`, conv1_2): the same stack with the vertical shift moved to dZ -- sum_p dZ[p] X[p + (dy, dx)]
+// X on M with a narrow dZ (`zstack`: side_prep, Cout = 16): the same stack with the vertical shift moved to dZ (below); its
+// 16 channels sit in 64-column blocks (TMA zero-fills the rest), so a kernel column is one N = 192 MMA instead of three
+// N = 16 ones (~51 cycles each: a narrow MMA is bound by reading its 128-row A tile).
+//
+// Cout <= 64 with X on M (`one_pass`: conv1_2, and side_prep by default): the stack with the vertical shift moved to dZ -- sum_p dZ[p] X[p + (dy, dx)]
 // = sum_q dZ[q - (dy, 0)] X[q + (0, dx)] -- so B = dZ halo box (three row shifts, N = 192) and A = X under two horizontal
 // shifts (two plain boxes LBO apart, M = 128).  Two MMAs per 16 pixels -- kernel columns (0, 1) and (2, ignored rows) --
 // cover all nine taps from ONE visit of the patch (3 X boxes + 1 dZ halo box = 68 KB), instead of six N = 64 MMAs in
-// each of two passes over both operands.
+// each of two passes over both operands.  Wider X is tiled by 64 channels (one work item each).
 //
 // Bias gradient db[co] = sum_p dZ[p][co]: the dZ boxes are in shared memory anyway, so the four epilogue
 // warps, otherwise idle until the accumulators are complete, sum them on the side; the CTAs that see the
@@ -68,6 +72,7 @@ struct WgParams {
   int c8;                    // first-layer mode (see the header comment)
   int stack;                 // N = 64 tile, X on N: the three kernel rows are one N = 192 MMA (LBO = one image row of the patch)
   int one_pass;              // Cin == Cout == 64: A = X under two column shifts, B = dZ under three row shifts, all taps per visit
+  int zstack;                // X on M, dZ (<= 64 channels) as ONE halo box whose three row shifts are one N = 192 MMA (one_pass, side_prep)
   int c8_lbo, c8_sbo;        // descriptor strides of its un-swizzled X operand (160 / 16)
   int debug;                 // FOSVOS_WG_DEBUG (timing experiments only): 1 = skip the reductions, 2 = no start rotation, 3 = no MMAs, 4 = no loads, 5 = neither, 6 = 5 + 1
 };
@@ -160,7 +165,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const int nb_x = p.x_is_a ? 2 : p.nb_n;
   const int nb_z = p.x_is_a ? p.nb_n : 2;
   const int x_off = p.x_is_a ? 0 : p.a_bytes;  // byte offset of the X boxes inside a stage
-  const int z_off = p.one_pass ? p.a_bytes + TW * 128 : p.x_is_a ? p.a_bytes : 0;   // (one_pass: the patch inside the dZ halo box)
+  const int z_off = p.zstack ? p.a_bytes + TW * 128 : p.x_is_a ? p.a_bytes : 0;   // (zstack: the patch inside the dZ halo box)
 
   if (warp == 0) {
     {
@@ -183,12 +188,13 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           }
         } else if (p.debug >= 4) {              // timing experiment: no loads
           if (ptx::elect_one()) ptx::mbar_arrive(&full_bar[stage]);
-        } else if (p.one_pass) {
+        } else if (p.zstack) {
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
-            for (int j = 0; j < 3; ++j)          // X through kernel column j (plain boxes), then the dZ halo box
-              ptx::tma_load_4d(st + j * WG_PLAIN_BLOCK, &map_x, &full_bar[stage], 0, x0 + j - 1, y0, n);
-            ptx::tma_load_4d(st + p.a_bytes, &map_z, &full_bar[stage], 0, x0, y0 - 1, n);
+            // plain X boxes: one_pass = the 64 channels through kernel columns 0..2; else the tile's two channel blocks through column s
+            for (int j = 0; j < (p.one_pass ? 3 : 2); ++j)
+              ptx::tma_load_4d(st + j * WG_PLAIN_BLOCK, &map_x, &full_bar[stage], p.one_pass ? mt * 64 : xc0 + 64 * j, x0 + (p.one_pass ? j : s) - 1, y0, n);
+            ptx::tma_load_4d(st + p.a_bytes, &map_z, &full_bar[stage], 0, x0, y0 - 1, n);      // the dZ halo box
           }
         } else if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full_bar[stage], p.stage_bytes);
@@ -206,7 +212,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       // kind::f16, D fp32, A/B bf16, both MN-major (bits 15/16), M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t lbo_a = (p.x_is_a && !p.one_pass) ? p.x_block : WG_PLAIN_BLOCK;
+      const uint32_t lbo_a = (p.x_is_a && !p.zstack) ? p.x_block : WG_PLAIN_BLOCK;
       const uint32_t lbo_b = p.x_is_a ? WG_PLAIN_BLOCK : p.x_block;
       const uint32_t tap_bytes = (uint32_t)TW * 128;       // one image row of the patch
       int stage = 0;
@@ -231,7 +237,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             ptx::umma_commit(&empty_bar[stage]);
             if (pt == p_end - 1) ptx::umma_commit(done_bar);
           }
-        } else if (p.one_pass || p.stack) {
+        } else if (p.zstack || p.stack) {
           if (ptx::elect_one()) {
             const uint32_t idesc192 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(192 >> 3) << 17);
             if (p.debug != 3 && p.debug < 5) {
@@ -349,19 +355,43 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         for (int ai = 0; ai < 6; ++ai) {
           const int a = ((ai + rot) % 6) / 3, i = (ai + rot) % 3;
           const int sj = a ? 2 : (row >> 6);
-          const bool ok = p.debug != 1 && p.debug != 6 && (a == 0 || row < 64);
-          float* dst = p.ws + ((long long)((2 - i) * 3 + sj) * p.Mtot + (row & 63)) * p.Ntot;
+          const int ci = mt * 64 + (row & 63);              // (one_pass tiles the X channels by 64: m_tiles = CinP / 64)
+          const bool ok = p.debug != 1 && p.debug != 6 && (a == 0 || row < 64) && ci < p.Mtot;
+          float* dst = p.ws + ((long long)((2 - i) * 3 + sj) * p.Mtot + ci) * p.Ntot;
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + a * 192 + i * 64;
 #pragma unroll 1
-          for (int c0 = 0; c0 < 64; c0 += 16) {
+          for (int c0 = 0; c0 < p.Ntot; c0 += 16) {
             uint32_t v[16];
             ptx::tmem_ld16(taddr + c0, v);
             ptx::tmem_ld_wait();
             if (ok) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                red_add_v4(dst + c0 + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                           __uint_as_float(v[4 * q + 3]));
+              for (int q = 0; q < 4; ++q) {
+                if (c0 + 4 * q < p.Ntot)
+                  red_add_v4(dst + c0 + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                             __uint_as_float(v[4 * q + 3]));
+              }
+            }
+          }
+        }
+      } else if (p.zstack) {
+        // column block i = the dZ box shifted down by i rows = kernel row 2 - i; the Ntot (<= 64) real channels lead each block
+        for (int ii = 0; ii < 3; ++ii) {
+          const int i = (ii + rot) % 3;
+          float* dst = p.ws + ((long long)((2 - i) * 3 + s) * p.Mtot + m0 + row) * p.Ntot;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + i * 64;
+#pragma unroll 1
+          for (int c0 = 0; c0 < p.Ntot; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld16(taddr + c0, v);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (c0 + 4 * q < p.Ntot)
+                  red_add_v4(dst + c0 + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                             __uint_as_float(v[4 * q + 3]));
+              }
             }
           }
         }
@@ -706,12 +736,15 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   p.Ntot = p.x_is_a ? CoutP : CinP;
   p.c8 = (CinP == 8 && !p.x_is_a && !getenv("FOSVOS_WG_NO_C8")) ? 1 : 0;
   static const bool no_stack = getenv("FOSVOS_WG_NO_STACK") != nullptr;      // A/B switch (timing experiments)
-  p.one_pass = (p.x_is_a && CinP == 64 && CoutP == 64 && !no_stack) ? 1 : 0;
+  // (narrow Cout, side_prep: 170 -> 162 us per window against three `zstack` passes; FOSVOS_WG_SIDE_THREE_PASSES selects those)
+  static const bool side_one_pass = getenv("FOSVOS_WG_SIDE_THREE_PASSES") == nullptr;
+  p.one_pass = (p.x_is_a && !no_stack && ((CinP == 64 && CoutP == 64) || (side_one_pass && CoutP <= 64 && CoutP % 4 == 0))) ? 1 : 0;
   p.c8_lbo = WG_C8_ROW; p.c8_sbo = 16;
   p.n_cols = p.c8 ? 32 : p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
   p.nb_n = (p.n_cols + 63) / 64;
   p.stack = (!p.x_is_a && !p.c8 && p.Ntot == 64 && !no_stack) ? 1 : 0;
-  p.m_tiles = ceil_div(p.Mtot, 128);
+  p.zstack = (p.one_pass || (p.x_is_a && p.Ntot <= 64 && p.Ntot % 4 == 0 && !no_stack)) ? 1 : 0;
+  p.m_tiles = ceil_div(p.Mtot, p.one_pass ? 64 : 128);
   p.n_tiles = ceil_div(p.Ntot, p.n_cols);
   // 128-pixel patch with TW % 8 == 0 that wastes the fewest out-of-frame pixels
   int best = 3; long long best_area = -1;
@@ -728,8 +761,9 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   p.patches = N * p.tiles_x * p.tiles_y;
   p.x_block = (TH + 2) * TW * 128;
   const int nb_x = p.x_is_a ? 2 : p.nb_n, nb_z = p.x_is_a ? p.nb_n : 2;
-  // one_pass: X as three plain boxes (kernel columns), dZ as ONE halo box (kernel rows)
-  const int x_bytes = p.c8 ? WG_C8_BYTES : p.one_pass ? 3 * WG_PLAIN_BLOCK : nb_x * p.x_block, z_bytes = p.one_pass ? p.x_block : nb_z * WG_PLAIN_BLOCK;
+  // zstack: X as plain boxes, dZ as ONE halo box (kernel rows)
+  const int x_bytes = p.c8 ? WG_C8_BYTES : p.zstack ? (p.one_pass ? 3 : 2) * WG_PLAIN_BLOCK : nb_x * p.x_block;
+  const int z_bytes = p.zstack ? p.x_block : nb_z * WG_PLAIN_BLOCK;
   p.a_bytes = p.x_is_a ? x_bytes : z_bytes;
   p.stage_bytes = x_bytes + z_bytes;
   p.stages = min(6, (220 * 1024 - 2048) / p.stage_bytes);
@@ -776,9 +810,9 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   }
 
   CUtensorMap mx, mz;
-  int rc = p.c8 ? wg_encode_c8(&mx, x, N, H, W) : wg_encode(&mx, x, N, H, W, CinP, TW, p.one_pass ? TH : TH + 2);
+  int rc = p.c8 ? wg_encode_c8(&mx, x, N, H, W) : wg_encode(&mx, x, N, H, W, CinP, TW, p.zstack ? TH : TH + 2);
   if (rc) return rc;
-  rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, p.one_pass ? TH + 2 : TH);
+  rc = wg_encode(&mz, dz, N, H, W, CoutP, TW, p.zstack ? TH + 2 : TH);
   if (rc) return rc;
 
   const int smem_bytes = p.stages * p.stage_bytes + 1024 + 1024;

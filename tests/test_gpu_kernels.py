@@ -321,7 +321,8 @@ def test_conv3x3_wgrad(dt, case):
 
 @pytest.mark.parametrize("case", [(1, 16, 24, 64, 64), (1, 17, 23, 64, 128), (2, 9, 30, 128, 16), (1, 33, 40, 256, 256),
                                   (1, 30, 54, 512, 512), (1, 12, 20, 40, 72), (1, 8, 8, 128, 128), (2, 17, 23, 128, 256),
-                                  (3, 20, 27, 256, 512), (2, 21, 37, 64, 64), (2, 13, 50, 64, 128), (1, 40, 40, 64, 256)])
+                                  (3, 20, 27, 256, 512), (2, 21, 37, 64, 64), (2, 13, 50, 64, 128), (1, 40, 40, 64, 256),
+                                  (1, 20, 21, 256, 24), (1, 12, 13, 64, 16), (2, 30, 54, 512, 16)])
 def test_conv3x3_wgrad_tc(case):
     """tcgen05 weight gradient (MN-major operands, halo-box tap reuse, split-K reductions).  Cout % 256 == 0 with
     Cin % 128 == 0 runs the CTA-pair kernel (cta_group::2, M = 256 over the two SMs of a TPC); Cin = 64 runs the row-stacked
