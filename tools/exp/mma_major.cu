@@ -47,7 +47,7 @@ constexpr int OPER = 192 * 1024;     // A region 64 KB, B region 128 KB
 constexpr int THREADS = 64;
 
 // a_mn / b_mn: 1 = MN-major operand.  N = columns of the whole MMA (CG == 2: each CTA holds N / 2 of them).
-template <int CG> __global__ void __launch_bounds__(THREADS, 1) major_kernel(int N, int a_mn, int b_mn, int n_acc, int n_mma, long long* out_cycles) {
+template <int CG, int a_mn, int b_mn> __global__ void __launch_bounds__(THREADS, 1) major_kernel(int N, int n_acc, int n_mma, long long* out_cycles) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   uint64_t* done = (uint64_t*)(smem + OPER);
@@ -83,20 +83,31 @@ template <int CG> __global__ void __launch_bounds__(THREADS, 1) major_kernel(int
     long long t0 = clock64();
     if (rank == 0) {
       if (elect_one()) {
+        // descriptors of the two operand regions the stream alternates between, built once: the issue loop only adds the
+        // (compile-time) offset of the K step to the start-address field -- a single thread issues every MMA, and a loop that
+        // rebuilds 64-bit descriptors with run-time branches costs ~80 cycles per MMA by itself (first version of this file)
+        const int n_cta = N / CG;
+        uint64_t da0[2], db0[2];
+        for (int h = 0; h < 2; ++h) {
+          da0[h] = a_mn ? desc_mn(a0 + h * 32768, 16384) : desc_k(a0 + h * 32768);
+          db0[h] = b_mn ? desc_mn(b0 + h * 65536, 16384) : desc_k(b0 + h * 65536);
+        }
+        const uint32_t b_slab = (uint32_t)(n_cta * 128) >> 4;
+        uint32_t acc_i = 0;
         for (int i = 0; i < n_mma; i += 8) {
           // MN-major: one 16 KB block = 128 K rows of 64 elements; the 8 steps walk its 16-row slices (2 KB each);
           //   A spans 2 blocks (M = 128), B spans N_cta / 64 blocks, LBO = 16 KB.
           // K-major: one K = 64 slab (rows of 128 B); 4 steps of 32 B inside it, then the next slab (A 16 KB, B N_cta * 128 B further).
-          const int n_cta = N / CG;
-          const uint32_t a = a0 + ((i >> 3) & 1) * 32768;
-          const uint32_t b = b0 + ((i >> 3) & 1) * 65536;
+          const int h = (i >> 3) & 1;
+          const uint32_t d_acc = tmem + acc_i * (uint32_t)N;
+          const uint32_t first = i >= 8 * n_acc;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint64_t da = a_mn ? desc_mn(a + k * 2048, 16384) : desc_k(a + (k >> 2) * 16384 + (k & 3) * 32);
-            const uint64_t db = b_mn ? desc_mn(b + k * 2048, 16384) : desc_k(b + (k >> 2) * (n_cta * 128) + (k & 3) * 32);
-            const uint32_t acc_off = (uint32_t)((i >> 3) % n_acc) * (uint32_t)N;
-            umma<CG>(tmem + acc_off, da, db, idesc, i >= 8 * n_acc || k != 0);
+            const uint64_t da = da0[h] + (a_mn ? (uint64_t)(k * 2048 >> 4) : (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4));
+            const uint64_t db = db0[h] + (b_mn ? (uint64_t)(k * 2048 >> 4) : (uint64_t)((k >> 2) * b_slab + (((k & 3) * 32) >> 4)));
+            umma<CG>(d_acc, da, db, idesc, k != 0 ? 1u : first);
           }
+          if (++acc_i == (uint32_t)n_acc) acc_i = 0;
         }
         commit<CG>(&done[0]);
       }
@@ -114,37 +125,37 @@ template <int CG> __global__ void __launch_bounds__(THREADS, 1) major_kernel(int
   }
 }
 
-template <int CG> static void run(int N, int a_mn, int b_mn, int n_acc) {
+template <int CG, int A_MN, int B_MN> static void run(int N, int n_acc) {
   long long* d;
   cudaMalloc(&d, 148 * sizeof(long long));
   cudaMemset(d, 0, 148 * sizeof(long long));
   const int smem = OPER + 2048;
-  cudaFuncSetAttribute(major_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(major_kernel<CG, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int n_mma = 8192;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(148); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, major_kernel<CG>, N, a_mn, b_mn, n_acc, n_mma, d);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, major_kernel<CG, A_MN, B_MN>, N, n_acc, n_mma, d);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
   long long h[148];
   cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
   const double cyc = mx / (double)n_mma;
-  printf("cta_group::%d M=%d N=%3d A %s B %s accs=%d: %6.1f cycles/MMA  (tensor work %d cycles; %.0f %% of peak)\n", CG, 128 * CG, N, a_mn ? "MN" : "K ",
-         b_mn ? "MN" : "K ", n_acc, cyc, N / 2, 100.0 * (N / 2) / cyc);
+  printf("cta_group::%d M=%d N=%3d A %s B %s accs=%d: %6.1f cycles/MMA  (tensor work %d cycles; %.0f %% of peak)\n", CG, 128 * CG, N, A_MN ? "MN" : "K ",
+         B_MN ? "MN" : "K ", n_acc, cyc, N / 2, 100.0 * (N / 2) / cyc);
   cudaFree(d);
 }
 
+template <int CG> static void sweep(int N, int n_acc) {
+  run<CG, 0, 0>(N, n_acc); run<CG, 0, 1>(N, n_acc); run<CG, 1, 0>(N, n_acc); run<CG, 1, 1>(N, n_acc);
+}
+
 int main() {
-  for (int N : {64, 128, 256})
-    for (int a_mn : {0, 1})
-      for (int b_mn : {0, 1}) run<1>(N, a_mn, b_mn, N == 256 ? 2 : 3);
-  run<1>(128, 1, 1, 1);
-  for (int N : {128, 256})
-    for (int a_mn : {0, 1})
-      for (int b_mn : {0, 1}) run<2>(N, a_mn, b_mn, N == 256 ? 2 : 3);
+  for (int N : {16, 48, 64, 96, 128, 192, 256}) sweep<1>(N, N >= 192 ? 2 : 3);
+  run<1, 1, 1>(128, 1);
+  for (int N : {64, 128, 192, 256}) sweep<2>(N, N >= 192 ? 2 : 3);
   return 0;
 }
