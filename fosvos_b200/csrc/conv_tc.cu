@@ -48,6 +48,11 @@
 
 namespace fosvos {
 
+// conv_stack_tc.cu
+bool conv_stack_tc_supported(int Cin, int Cout);
+int conv_stack_tc_launch(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, int N, int H,
+                         int W, int Cin, int relu, cudaStream_t stream);
+
 constexpr int TC_BM = 128;       // pixels per tile
 constexpr int TC_BK = 64;        // channels per K slab (128 B of bf16 = one swizzle row)
 constexpr int TC_EPI_WARPS = 16;   // two groups of eight
@@ -851,6 +856,16 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   FOSVOS_REQUIRE(!(flags & FOSVOS_CONV_MASK) || mask, "%s: MASK flag without mask pointer", what);
   FOSVOS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0,
                  "%s: pointers must be 16-byte aligned", what);
+  // 64 output channels (conv1_2 forward, the data gradients of conv1_2 / conv2_1): the row-stacked kernel of conv_stack_tc.cu
+  // (three taps per N = 192 MMA instead of three operand-read-bound N = 64 ones)
+  // (its epilogue -- two shuffles per output element -- outlasts the MMAs of a ONE-slab tile when it also reads a mask:
+  //  conv1_2's data gradient, 205 us against 186 us at batch 5, stays on the generic kernel; FOSVOS_TC_STACK_ALL overrides)
+  if (!split && taps == 9 && conv_stack_tc_supported(Cin, Cout) && !(flags & FOSVOS_CONV_ACCUMULATE) &&
+      (!(flags & FOSVOS_CONV_MASK) || Cin >= 128 || getenv("FOSVOS_TC_STACK_ALL")) &&
+      !((flags & FOSVOS_CONV_MASK) && (flags & FOSVOS_CONV_RELU)) && (((uintptr_t)mask | (uintptr_t)y | (uintptr_t)y_pool) & 31) == 0 &&      // its epilogue moves 32 bytes per access
+      !getenv("FOSVOS_TC_NO_STACK"))
+    return conv_stack_tc_launch(x, w_packed, (flags & FOSVOS_CONV_BIAS) ? bias : nullptr, (flags & FOSVOS_CONV_MASK) ? mask : nullptr, y, y_pool, N,
+                                H, W, Cin, (flags & FOSVOS_CONV_RELU) ? 1 : 0, as_stream(stream));
   TcParams p;
   p.bias = bias;
   p.mask = (const __nv_bfloat16*)mask;

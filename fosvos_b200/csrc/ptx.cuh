@@ -273,6 +273,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 32-byte global accesses (sm_100: LDG/STG.256): one full sector per lane and instruction; addr must be 32-byte aligned
+__device__ __forceinline__ void ldg256_nc(const void* addr, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(addr));
+}
+__device__ __forceinline__ void stg256(void* addr, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // n / d for 0 <= n < 2^31 with d's precomputed (mul, shift): q = (umulhi(mul, n) + n) >> shift
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shift) { return (__umulhi(mul, n) + n) >> shift; }
 

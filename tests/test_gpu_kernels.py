@@ -199,6 +199,62 @@ def test_conv3x3_pool_only(case):
     assert torch.equal(yp, p_ref)
 
 
+STACK_CASES = [
+    # N, H, W, Cin (Cout = 64): tile = 14 x 8 outputs; widths / heights around the tile edges, odd sizes for the ceil-mode pool
+    (1, 33, 45, 64), (2, 16, 28, 64), (1, 9, 13, 64), (1, 8, 15, 128), (3, 17, 29, 128), (1, 1, 1, 64), (1, 2, 14, 64), (1, 25, 57, 64),
+]
+
+
+@pytest.mark.parametrize("case", STACK_CASES)
+def test_conv3x3_row_stack_forward_and_pool(case, monkeypatch):
+    """Cout = 64 layers run the row-stacked kernel (conv_stack_tc.cu: three taps per N = 192 MMA, partial sums combined by
+    shuffles, pool fused with in-warp shuffles): against torch on the same rounded operands, and against the generic
+    tensor-core kernel (same bf16 operands, fp32 accumulation in a different order: equal up to one bf16 ulp)."""
+    n, h, w_, cin = case
+    g = _gen(61)
+    x = torch.randn(n, cin, h, w_, generator=g)
+    w = torch.randn(64, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(64, generator=g)
+    xd = _nhwc(x, torch.bfloat16)
+    wp = ops.pack_weight(w.to(DEV), L.W_TC_FWD, torch.bfloat16)
+    bp = ops.pad_bias(b.to(DEV), 64, DEV)
+    for flags, relu in ((L.CONV_BIAS | L.CONV_RELU, True), (L.CONV_BIAS, False), (0, False)):
+        y = ops.conv3x3(xd, wp, bp if flags & L.CONV_BIAS else None, 64, flags)
+        ref = _conv_ref(_bf16r(x), _bf16r(w), b if flags & L.CONV_BIAS else None, relu)
+        got = _nchw(y, 64)
+        assert torch.allclose(got, ref, rtol=2 ** -7, atol=2e-2), float((got - ref).abs().max())
+    flags = L.CONV_BIAS | L.CONV_RELU
+    y = ops.conv3x3(xd, wp, bp, 64, flags)
+    y2, yp = ops.conv3x3_pool(xd, wp, bp, 64, flags)
+    yp_only = ops.conv3x3_pool_only(xd, wp, bp, 64, flags)
+    assert torch.equal(y2, y)
+    assert torch.equal(yp, ops.maxpool2x2(y))
+    assert torch.equal(yp_only, yp)
+    monkeypatch.setenv("FOSVOS_TC_NO_STACK", "1")
+    y_gen = ops.conv3x3(xd, wp, bp, 64, flags)
+    monkeypatch.delenv("FOSVOS_TC_NO_STACK")
+    d = (y.float() - y_gen.float()).abs()
+    assert float((d / y_gen.float().abs().clamp_min(1e-2)).max()) <= 2 ** -7, float(d.max())
+
+
+@pytest.mark.parametrize("case", STACK_CASES)
+def test_conv3x3_row_stack_dgrad(case, monkeypatch):
+    """Data-gradient use of the row-stacked kernel (64 channels out): flipped / transposed weights, ReLU mask.
+    (By default only dZ with >= 128 channels takes it; the environment switch sends the 64-channel cases there too.)"""
+    monkeypatch.setenv("FOSVOS_TC_STACK_ALL", "1")
+    n, h, w_, cz = case                    # cz = channels of dZ (the forward conv's Cout); the forward Cin is 64
+    g = _gen(62)
+    xprev = torch.randn(n, 64, h, w_, generator=g).clamp_min(0)
+    wt = torch.randn(cz, 64, 3, 3, generator=g) * 0.05
+    dz = torch.randn(n, cz, h, w_, generator=g)
+    ref = F.conv_transpose2d(_bf16r(dz).double(), _bf16r(wt).double(), padding=1).float() * (_bf16r(xprev) > 0)
+    wp = ops.pack_weight(wt.to(DEV), L.W_TC_DGRAD, torch.bfloat16)
+    out = ops.conv3x3(_nhwc(dz, torch.bfloat16), wp, None, 64, L.CONV_MASK, mask=_nhwc(xprev, torch.bfloat16))
+    got = _nchw(out, 64)
+    assert torch.allclose(got, ref, rtol=2 ** -6, atol=5e-2), float((got - ref).abs().max())
+    assert (got[_bf16r(xprev) <= 0] == 0).all()
+
+
 SIDE_CASES = [
     # N, H, W, Cin: tile = 30 x 4 outputs; widths around the tile edge, one-pixel maps, ragged channel counts (pruned nets)
     (1, 30, 54, 512), (2, 15, 27, 512), (1, 45, 70, 128), (3, 7, 5, 64), (1, 4, 30, 256), (1, 5, 31, 128), (1, 3, 29, 64),
