@@ -11,7 +11,7 @@
 // an N = 192 instruction is tensor-bound (96 cycles for 96 of work) and replaces three N = 64 ones (144 cycles).
 // The three partial sums of an output pixel sit in neighbouring accumulator rows = neighbouring LANES of one warp and
 // are combined with two shuffles per channel; results go from registers straight to global memory (32-byte stores, made
-// line-contiguous by a register transpose inside groups of four lanes), so the epilogue uses no shared memory, whose
+// contiguous over lane pairs by a register exchange), so the epilogue uses no shared memory, whose
 // traffic would compete with the tensor core's operand reads (80 of the 96 cycles of an N = 192 MMA).
 //
 // Tile = 16 x 8 pixel patch whose first and last columns are halo (14 x 8 outputs, 87.5 % useful rows): GEMM row
@@ -21,9 +21,15 @@
 // 64-channel slab (TMA, SWIZZLE_128B; out-of-frame pixels zero-filled = the conv padding); vertical tap r is the
 // same tile read 16 * r rows further (2048 B, a multiple of the swizzle atom).  B operand: ALL weights of the layer
 // ([slab][r][(s, co)][64 ch]: 72 KB for Cin = 64, 144 KB for Cin = 128) are loaded once per persistent CTA and stay
-// resident.  Two TMEM accumulators (256 columns apart); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 / 6-9 =
-// two epilogue groups draining alternate tiles.
+// resident.  Two TMEM accumulators (256 columns apart); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 / 10-17 =
+// two epilogue groups draining alternate tiles (two warps per TMEM lane quadrant, 32 channels each).
 // Epilogues: forward = bias, ReLU, bf16 store and / or pooled store; data gradient = ReLU mask (mask[n, y, x, co] > 0).
+//
+// What bounds it (ncu, conv1_2 pool-only at batch 16: 405 us against 526 us for the generic kernel, tensor pipe 72 %): the
+// MIO data pipe (`l1tex__data_pipe_lsu_wavefronts` 80 %).  A tile's 128 x 192 fp32 accumulator is 768 wavefronts of
+// TMEM -> register traffic (three times the generic kernel's) and the shuffles add as many, together more than the
+// 1152 tensor cycles of a one-slab tile.  Two-slab tiles (conv2_1's data gradient: 72 us against 93 us) hide it.  Layers
+// that also read a mask at one slab (conv1_2's data gradient) stay on the generic kernel (conv_tc.cu dispatch).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -31,7 +37,7 @@
 
 namespace fosvos {
 
-constexpr int SK_THREADS = 64 + 8 * 32;
+constexpr int SK_THREADS = 64 + 16 * 32;
 constexpr int SK_TW = 16, SK_TH = 8;
 constexpr int SK_OUT_W = SK_TW - 2;                       // output columns per tile
 constexpr int SK_A_BYTES = (SK_TH + 2) * SK_TW * 128;     // 20480: halo box of one 64-channel slab
@@ -80,7 +86,7 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 4);            // one arrive per warp of the epilogue group
+      ptx::mbar_init(&tmem_empty[i], 8);            // one arrive per warp of the epilogue group
     }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_barrier_init();
@@ -158,8 +164,12 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     }
   } else {
     // ===================== epilogue: group g (warps 2 + 4 g ..) drains accumulator g = every other tile =====================
+    // sixteen warps: group (accumulator = every other tile) x channel half (32 of the 64 output channels) x TMEM lane quadrant.
+    // The epilogue is a long dependent chain per thread (TMEM load -> shuffles -> convert -> stores); with one warp per
+    // quadrant and group it took 2.3x the MMA time of a one-slab tile, so each quadrant's work is split over two warps.
     const int e = warp - 2;
-    const int grp = e >> 2;
+    const int grp = e >> 3;
+    const int cbase = 2 * ((e >> 2) & 1);               // first of this warp's two 16-channel chunks
     const int quad = warp & 3;                          // TMEM lane quadrant this warp may access = image rows 2 quad, 2 quad + 1
     const int as = grp;
     const int col = lane & 15, half = lane >> 4;
@@ -176,20 +186,20 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       // pooled output: written by the top-left pixel of each 2x2 window (even row = lower half-warp, even x = odd column)
       const bool pool_writer = p.y_pool && valid && half == 0 && (col & 1);
       const long long ppix = ((long long)n * PH + (gy >> 1)) * PW + (gx >> 1);
-      // Global accesses are made line-contiguous inside groups of four lanes (four horizontally adjacent pixels, 4 x 128 B):
-      // access k of lane 4g + j touches 16-channel chunk j of pixel 4g + k, so the four lanes cover ONE 128-byte line and a
-      // warp instruction 8 lines -- lane-per-pixel accesses (32 lines of 32 B each per instruction) kept the LSU as busy as the
-      // tensor core.  Registers are exchanged with a two-step butterfly (32 shuffles per tile for the stores, 8 for the masks).
-      const int j4 = lane & 3, g4 = lane & ~3;
+      // Global accesses are made contiguous inside lane PAIRS (two horizontally adjacent pixels, 2 x 64 B of this warp's
+      // channel half): access k of lane 2g + j touches chunk cbase + j of pixel 2g + k, so the two lanes cover 64 contiguous
+      // bytes and a warp instruction 16 half-lines -- lane-per-pixel accesses (32 lines of 32 B per instruction) kept the LSU
+      // as busy as the tensor core.  Registers are exchanged with one shuffle per register.
+      const int j2 = lane & 1, g2 = lane & ~1;
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-      // the ReLU mask (chunk j4 of the four pixels of the group), requested BEFORE waiting for the accumulator: its DRAM
+      // the ReLU mask (chunk cbase + j2 of the two pixels of the pair), requested BEFORE waiting for the accumulator: its DRAM
       // latency hides behind the tile's MMAs
-      uint32_t mk[4][8];
+      uint32_t mk[2][8];
       if (p.mask) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if ((vmask >> (g4 + k)) & 1u) {
-            ptx::ldg256_nc(p.mask + (pix - j4 + k) * 64 + j4 * 16, mk[k]);
+        for (int k = 0; k < 2; ++k) {
+          if ((vmask >> (g2 + k)) & 1u) {
+            ptx::ldg256_nc(p.mask + (pix - j2 + k) * 64 + (cbase + j2) * 16, mk[k]);
           } else {
 #pragma unroll
             for (int r = 0; r < 8; ++r) mk[k][r] = 0u;
@@ -198,12 +208,12 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       }
       ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
       ptx::tc_fence_after();
-      uint32_t mbits[4] = {0u, 0u, 0u, 0u};              // bit e of mbits[c]: mask[own pixel][16 c + e] > 0
+      uint32_t mbits[2] = {0u, 0u};                      // bit e of mbits[c]: mask[own pixel][16 (cbase + c) + e] > 0
       if (p.mask) {
-        // 16 "positive" bits per (pixel k, chunk j4), packed two pixels per word, then handed to the lanes that own the pixels
-        uint32_t w[2] = {0u, 0u};
+        // 16 "positive" bits per (pixel k, chunk cbase + j2), both pixels in one word, then handed to the lanes that own the pixels
+        uint32_t w = 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 2; ++k) {
           uint32_t bits = 0u;
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
@@ -211,25 +221,22 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             bits |= (((mw & 0x8000u) == 0 && (mw & 0x7fffu) != 0) ? 1u : 0u) << (2 * r);
             bits |= (((mw & 0x80000000u) == 0 && (mw & 0x7fff0000u) != 0) ? 1u : 0u) << (2 * r + 1);
           }
-          w[k >> 1] |= bits << (16 * (k & 1));
+          w |= bits << (16 * k);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], g4 + c), w1 = __shfl_sync(0xffffffffu, w[1], g4 + c);
-          mbits[c] = (((j4 & 2) ? w1 : w0) >> (16 * (j4 & 1))) & 0xffffu;
-        }
+        for (int c = 0; c < 2; ++c) mbits[c] = (__shfl_sync(0xffffffffu, w, g2 + c) >> (16 * j2)) & 0xffffu;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * SK_ACC_STRIDE;
-      uint32_t o[4][8];
+      uint32_t o[2][8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = 16 * c;
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = 16 * (cbase + c);
         uint32_t d0[16], d1[16], d2[16];
         ptx::tmem_ld16(taddr + c0, d0);
         ptx::tmem_ld16(taddr + 64 + c0, d1);
         ptx::tmem_ld16(taddr + 128 + c0, d2);
         ptx::tmem_ld_wait();
-        if (c == 3) {                                         // last read of the accumulator: hand it back before the arithmetic
+        if (c == 1) {                                         // last read of the accumulator: hand it back before the arithmetic
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
@@ -270,31 +277,17 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         }
       }
       if (p.y) {
-        // 4 x 4 transpose of 32-byte items inside the lane group: o[c] (own pixel, chunk c) -> f[k] (pixel 4g + k, chunk j4)
-        const bool b0 = j4 & 1, b1 = j4 & 2;
-        uint32_t a[2][2][8];            // after step 1: a[m][q] = chunk 2 m + b0 of pixel (j4 & ~1) + q
+        // 2 x 2 transpose of 32-byte items inside the lane pair: o[c] (own pixel, chunk cbase + c) -> f[k] (pixel 2g + k, chunk cbase + j2)
+        uint32_t f[2][8];
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const uint32_t recv = __shfl_xor_sync(0xffffffffu, b0 ? o[2 * m][r] : o[2 * m + 1][r], 1);
-            a[m][0][r] = b0 ? recv : o[2 * m][r];
-            a[m][1][r] = b0 ? o[2 * m + 1][r] : recv;
-          }
-        }
-        uint32_t f[4][8];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const uint32_t recv = __shfl_xor_sync(0xffffffffu, b1 ? a[0][q][r] : a[1][q][r], 2);
-            f[q][r] = b1 ? recv : a[0][q][r];
-            f[2 + q][r] = b1 ? a[1][q][r] : recv;
-          }
+        for (int r = 0; r < 8; ++r) {
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, j2 ? o[0][r] : o[1][r], 1);
+          f[0][r] = j2 ? recv : o[0][r];
+          f[1][r] = j2 ? o[1][r] : recv;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if ((vmask >> (g4 + k)) & 1u) ptx::stg256(p.y + (pix - j4 + k) * 64 + j4 * 16, f[k]);
+        for (int k = 0; k < 2; ++k)
+          if ((vmask >> (g2 + k)) & 1u) ptx::stg256(p.y + (pix - j2 + k) * 64 + (cbase + j2) * 16, f[k]);
       }
     }
   }

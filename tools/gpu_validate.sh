@@ -21,7 +21,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 echo "ncu launches inf rc=$?"
 elif [ "$PART" = b ]; then
 timeout 120 python tools/profile_step.py 3 16 inf > gpurun_out/plain.log 2>&1 &&
-timeout 700 ncu --set full --clock-control none -k regex:"conv3x3_tc_kernel|conv3x3_side_tc_kernel" -s 34 -c 17 -o gpurun_out/prof_conv_$TAG -f python tools/profile_step.py 3 16 inf > gpurun_out/ncu_full1.log 2>&1
+timeout 700 ncu --set full --clock-control none -k regex:"conv3x3_tc_kernel|conv3x3_side_tc_kernel|conv3x3_stack_tc_kernel" -s 34 -c 17 -o gpurun_out/prof_conv_$TAG -f python tools/profile_step.py 3 16 inf > gpurun_out/ncu_full1.log 2>&1
 echo "ncu full conv rc=$?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"side_upsample_sep2" -s 4 -c 1 -o gpurun_out/prof_side_$TAG -f python tools/side_sep_probe.py 16 > gpurun_out/ncu_side.log 2>&1
 echo "ncu full side rc=$?"
