@@ -4,6 +4,8 @@
 //                       [ci][8-tap][co64] layouts) and the padded fp32 bias from the updated fp32 parameters
 // (reference: optimizer.step() / zero_grad() at train_online.py:99-100; the packed copies are derived data).
 // Both are HBM-bound tile transposes through shared memory: every global access is a contiguous run.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fosvos {
@@ -119,8 +121,9 @@ repack_kernel(const fosvos_repack_entry* __restrict__ table, int n_entries, cons
 //   packed bf16 forward / data-gradient copies and the padded bias refreshed from the new p
 // Moves 28 B per parameter (ws read + zeroed, p and buf read + written, 2 x 2 B packed) instead of the 48 B of the three
 // separate launches.
-__global__ void __launch_bounds__(256)
-conv_step_kernel(const fosvos_convstep_entry* __restrict__ table, int n_entries, const int* __restrict__ prefix, int n_tiles, float mu) {
+__global__ void __launch_bounds__(256, 3)
+conv_step_kernel(const fosvos_convstep_entry* __restrict__ table, int n_entries, const int* __restrict__ prefix, int n_tiles, float mu,
+                 int allow_vec) {
   constexpr int PITCH = PACK_CI * 9 + 1;
   __shared__ float sm[PACK_CO * PITCH];
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -131,6 +134,78 @@ conv_step_kernel(const fosvos_convstep_entry* __restrict__ table, int n_entries,
     const int co0 = (local / ci_tiles) * PACK_CO, ci0 = (local % ci_tiles) * PACK_CI;
     const int nco = min(PACK_CO, e.Cout - co0), nci = min(PACK_CI, e.Cin - ci0);
     const long long plane = (long long)e.CoutP * e.CinP;
+    // Full tiles (all but the channel tails and the first layer) move 16 bytes per access: the workspace rows, the OIHW runs
+    // (32 x 9 floats per cout) and hence every global access of steps 1 and 2 are float4-aligned there.
+    const bool vec = allow_vec && nco == PACK_CO && nci == PACK_CI && (e.Cin & 3) == 0 && (e.CinP & 3) == 0 && (e.CoutP & 3) == 0 &&
+                     (((uintptr_t)e.ws | (uintptr_t)e.w | (uintptr_t)e.buf | (uintptr_t)e.dw) & 15) == 0;
+    if (vec) {
+      // 1. nine float4 per thread (one per tap), all loads before the stores that clear them
+      static_assert(PACK_CO == 32 && PACK_CI == 32, "vector path: 8 float4 per row, 32 rows = 256 threads");
+      const int q = threadIdx.x & 7, row = threadIdx.x >> 3;          // row = cout (x_is_a = 0) or cin (x_is_a = 1) of the tile
+      float* base = e.ws + (e.x_is_a ? ((long long)(ci0 + row) * e.CoutP + co0) : ((long long)(co0 + row) * e.CinP + ci0)) + 4 * q;
+      float4 g4[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) g4[tap] = *reinterpret_cast<const float4*>(base + tap * plane);
+      // step 2's operands (32 runs of 288 contiguous floats = 2304 float4, nine per thread in three batches) do not depend on
+      // step 1: the first batch is requested now, every further one while its predecessor is processed, so a tile costs
+      // ~3 dependent DRAM round trips instead of 5 (the kernel is latency-bound: 3 blocks of 8 warps per SM)
+      float4 pv[3], bv[3];
+      long long gi[3];
+      int si[3];
+      auto request = [&](int b, float4 (&p4)[3], float4 (&b4)[3], long long (&g)[3], int (&sidx)[3]) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int idx = threadIdx.x + 256 * (3 * b + u);
+          const int co_l = idx / 72, r4 = idx - co_l * 72;
+          g[u] = ((long long)(co0 + co_l) * e.Cin + ci0) * 9 + 4 * r4;
+          sidx[u] = co_l * PITCH + 4 * r4;
+          p4[u] = *reinterpret_cast<const float4*>(e.w + g[u]);
+          b4[u] = *reinterpret_cast<const float4*>(e.buf + g[u]);
+        }
+      };
+      request(0, pv, bv, gi, si);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        *reinterpret_cast<float4*>(base + tap * plane) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float gv[4] = {g4[tap].x, g4[tap].y, g4[tap].z, g4[tap].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int co_l = e.x_is_a ? 4 * q + j : row, ci_l = e.x_is_a ? row : 4 * q + j;
+          sm[co_l * PITCH + ci_l * 9 + tap] = gv[j];
+        }
+      }
+      __syncthreads();
+      // 2. SGD with momentum; the new weights replace the gradient in smem
+      const float lr = e.lr, wd = e.weight_decay;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float4 pn4[3], bn4[3];
+        long long gn[3];
+        int sn[3];
+        if (b < 2) request(b + 1, pn4, bn4, gn, sn);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const float4 dv = e.dw ? *reinterpret_cast<const float4*>(e.dw + gi[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, b4[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+          const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+          float bn[4], pn[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float gv = sm[si[u] + j] + d4[j];
+            bn[j] = mu * b4[j] + (gv + wd * p4[j]);
+            pn[j] = p4[j] - lr * bn[j];
+            sm[si[u] + j] = pn[j];
+          }
+          *reinterpret_cast<float4*>(e.buf + gi[u]) = make_float4(bn[0], bn[1], bn[2], bn[3]);
+          *reinterpret_cast<float4*>(e.w + gi[u]) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+          if (e.dw) *reinterpret_cast<float4*>(e.dw + gi[u]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (b < 2) {
+#pragma unroll
+          for (int u = 0; u < 3; ++u) { pv[u] = pn4[u]; bv[u] = bn4[u]; gi[u] = gn[u]; si[u] = sn[u]; }
+        }
+      }
+    } else {
     // 1. gather the accumulator tile (fastest index = the workspace's contiguous dimension) and clear it.  Loads are issued
     // in batches of six BEFORE the stores that clear them: the compiler cannot move a load across an earlier store to the
     // same array, and one load in flight per thread left the kernel latency-bound (2.4 TB/s)
@@ -194,6 +269,7 @@ conv_step_kernel(const fosvos_convstep_entry* __restrict__ table, int n_entries,
         }
       }
     }
+    }
     if (ci0 == 0 && e.bias_out && threadIdx.x < nco)
       e.bias_out[co0 + threadIdx.x] = e.bias ? e.bias[co0 + threadIdx.x] : 0.f;
     __syncthreads();
@@ -241,7 +317,8 @@ extern "C" {
 int fosvos_conv_step_all(const fosvos_convstep_entry* table, int n_entries, const int* tile_prefix, int n_tiles, float momentum,
                          fosvos_stream_t stream) {
   FOSVOS_REQUIRE(table && tile_prefix && n_entries > 0 && n_tiles > 0, "conv_step_all: bad arguments");
-  conv_step_kernel<<<min(n_tiles, num_sms() * 6), 256, 0, as_stream(stream)>>>(table, n_entries, tile_prefix, n_tiles, momentum);
+  static const int allow_vec = getenv("FOSVOS_STEP_NO_VEC") ? 0 : 1;          // A/B switch (timing experiments)
+  conv_step_kernel<<<min(n_tiles, num_sms() * 6), 256, 0, as_stream(stream)>>>(table, n_entries, tile_prefix, n_tiles, momentum, allow_vec);
   return check_launch("conv_step_all");
 }
 

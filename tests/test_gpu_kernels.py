@@ -441,15 +441,21 @@ def test_fused_conv_step_equals_fold_sgd_repack():
         st.append(dict(cout=cout, cin=cin, cinp=cinp, coutp=coutp, lr=1e-3 * (k + 1), wd=2e-4 if k % 2 == 0 else 0.0,
                        w_a=w.clone(), w_b=w.clone(), buf_a=torch.zeros_like(w), buf_b=torch.zeros_like(w), bias=b,
                        ws_a=ops.wgrad_workspace(cinp, coutp, DEV), ws_b=ops.wgrad_workspace(cinp, coutp, DEV),
-                       dw=torch.zeros_like(w),
+                       dw=torch.zeros_like(w), dw_b=torch.zeros_like(w),
                        fwd_a=ops.pack_weight(w, L.W_TC_FWD, torch.bfloat16), dgr_a=ops.pack_weight(w, L.W_TC_DGRAD, torch.bfloat16),
                        fwd_b=ops.pack_weight(w, L.W_TC_FWD, torch.bfloat16), dgr_b=ops.pack_weight(w, L.W_TC_DGRAD, torch.bfloat16),
                        bo_a=ops.pad_bias(None, cout, DEV), bo_b=ops.pad_bias(None, cout, DEV)))
     fold_t = ops.fold_table([(e["ws_a"], e["dw"]) for e in st], DEV)
     sgd_t = ops.sgd_table([(e["w_a"], e["dw"], e["buf_a"], e["lr"], e["wd"]) for e in st], DEV)
     rep_t = ops.repack_table([(e["w_a"], e["bias"], e["fwd_a"], e["dgr_a"], e["bo_a"]) for e in st], DEV)
-    conv_t = ops.convstep_table([(e["ws_b"], None, e["w_b"], e["buf_b"], e["bias"], e["fwd_b"], e["dgr_b"], e["bo_b"], e["lr"], e["wd"]) for e in st], DEV)
+    # the fused step also takes a pending .grad (cleared like the accumulator): entries 1 and 3 carry one
+    conv_t = ops.convstep_table([(e["ws_b"], e["dw_b"] if k in (1, 3) else None, e["w_b"], e["buf_b"], e["bias"], e["fwd_b"], e["dgr_b"], e["bo_b"],
+                                  e["lr"], e["wd"]) for k, e in enumerate(st)], DEV)
     for step in range(2):
+        for k, e in enumerate(st):
+            if k in (1, 3):
+                e["dw"].copy_(torch.randn(e["dw"].shape, generator=g) * 0.01)
+                e["dw_b"].copy_(e["dw"])
         for e in st:
             x = _nhwc(_bf16r(torch.randn(1, e["cin"], 10, 16, generator=g)), torch.bfloat16)
             dz = _nhwc(_bf16r(torch.randn(1, e["cout"], 10, 16, generator=g)), torch.bfloat16)
@@ -460,7 +466,7 @@ def test_fused_conv_step_equals_fold_sgd_repack():
         ops.repack_all(rep_t)
         ops.conv_step_all(conv_t, mu)
         for e in st:
-            assert float(e["ws_b"].abs().max()) == 0.0
+            assert float(e["ws_b"].abs().max()) == 0.0 and float(e["dw_b"].abs().max()) == 0.0
             assert torch.allclose(e["w_b"], e["w_a"], rtol=1e-6, atol=1e-7), (step, float((e["w_b"] - e["w_a"]).abs().max()))
             assert torch.allclose(e["buf_b"], e["buf_a"], rtol=1e-6, atol=1e-7)
             assert torch.equal(e["bo_b"], e["bo_a"])
@@ -468,7 +474,8 @@ def test_fused_conv_step_equals_fold_sgd_repack():
             assert float((e["fwd_b"].float() - e["fwd_a"].float()).abs().max()) <= 2 ** -7 * float(e["w_a"].abs().max())
             assert float((e["dgr_b"].float() - e["dgr_a"].float()).abs().max()) <= 2 ** -7 * float(e["w_a"].abs().max())
     # in-place rewrite of the table (new learning rates) keeps its device buffer
-    conv_t2 = ops.convstep_table([(e["ws_b"], None, e["w_b"], e["buf_b"], e["bias"], e["fwd_b"], e["dgr_b"], e["bo_b"], 2 * e["lr"], e["wd"]) for e in st], DEV, out=conv_t)
+    conv_t2 = ops.convstep_table([(e["ws_b"], e["dw_b"] if k in (1, 3) else None, e["w_b"], e["buf_b"], e["bias"], e["fwd_b"], e["dgr_b"], e["bo_b"],
+                                   2 * e["lr"], e["wd"]) for k, e in enumerate(st)], DEV, out=conv_t)
     assert conv_t2[0].data_ptr() == conv_t[0].data_ptr()
 
 
