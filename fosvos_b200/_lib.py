@@ -34,6 +34,7 @@ SIGNATURES = {
     "fosvos_conv3x3_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_tc_pool": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_conv3x3_tc_pool_arg": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fosvos_conv3x3_side_tc_supported": (_i, [_i]),
     "fosvos_conv3x3_side_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fosvos_split_pairs": (_i, [_i]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "fosvos_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_maxpool2x2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_maxpool2x2_bwd_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fosvos_maxpool2x2_bwd_arg": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fosvos_side_params_bytes": (C.c_size_t, []),
     "fosvos_side_workspace_bytes": (C.c_size_t, [_vp, _vp, _i]),
     "fosvos_side_upsample_plan": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),

@@ -51,6 +51,7 @@ struct SkParams {
   const __nv_bfloat16* mask;     // (N, H, W, 64) or null
   __nv_bfloat16* y;              // (N, H, W, 64) or null (pool-only)
   __nv_bfloat16* y_pool;         // (N, ceil(H/2), ceil(W/2), 64) or null
+  uint32_t* pool_arg;            // (N, ceil(H/2), ceil(W/2), 2, 2) or null: window index of the first maximum, two bit planes per 32 channels
   int relu;
   int N, H, W;
   int tiles_x, tiles_y, total_tiles;
@@ -228,6 +229,7 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * SK_ACC_STRIDE;
       uint32_t o[2][8];
+      uint32_t arg_lo = 0u, arg_hi = 0u;                  // bit planes of the pool's window index, this warp's 32 channels
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = 16 * (cbase + c);
@@ -261,21 +263,34 @@ conv3x3_stack_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         }
         if (p.y_pool) {
           // 2x2 ceil-mode max of the bf16 results (post-ReLU, >= 0: an out-of-frame partner contributes 0)
+          // (row first, then the row below: with `pool_arg` the window index of the FIRST maximum in scan order is kept --
+          //  a later candidate wins only if strictly greater; non-negative bf16 compare as integers)
           uint32_t pl[8];
+          uint32_t right_wins = 0u, row2_wins = 0u;          // bit 2 j + h: channel c0 + 2 j + h
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t mine = valid ? o[c][j] : 0u;
-            const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&mine);
-            const uint32_t below = __shfl_xor_sync(0xffffffffu, mine, 16);
-            __nv_bfloat162 m = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(&below));
-            const uint32_t mu = *reinterpret_cast<const uint32_t*>(&m);
-            const uint32_t right = __shfl_down_sync(0xffffffffu, mu, 1);
-            m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(&right));
+            const uint32_t right = __shfl_down_sync(0xffffffffu, mine, 1);
+            __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&mine), *reinterpret_cast<const __nv_bfloat162*>(&right));
+            const uint32_t am = *reinterpret_cast<const uint32_t*>(&m);
+            const uint32_t below = __shfl_xor_sync(0xffffffffu, am, 16);
+            m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(&below));
             pl[j] = *reinterpret_cast<const uint32_t*>(&m);
+            if (p.pool_arg) {
+              right_wins |= ((right & 0xffffu) > (mine & 0xffffu) ? 1u : 0u) << (2 * j) | ((right >> 16) > (mine >> 16) ? 1u : 0u) << (2 * j + 1);
+              row2_wins |= ((below & 0xffffu) > (am & 0xffffu) ? 1u : 0u) << (2 * j) | ((below >> 16) > (am >> 16) ? 1u : 0u) << (2 * j + 1);
+            }
           }
           if (pool_writer) ptx::stg256(p.y_pool + ppix * 64 + c0, pl);
+          if (p.pool_arg) {
+            const uint32_t right_wins_below = __shfl_xor_sync(0xffffffffu, right_wins, 16);
+            arg_lo |= ((row2_wins & right_wins_below) | (~row2_wins & right_wins & 0xffffu)) << (16 * c);
+            arg_hi |= row2_wins << (16 * c);
+          }
         }
       }
+      if (p.pool_arg && pool_writer)
+        *reinterpret_cast<uint2*>(p.pool_arg + (ppix * 2 + (cbase >> 1)) * 2) = make_uint2(arg_lo, arg_hi);
       if (p.y) {
         // 2 x 2 transpose of 32-byte items inside the lane pair: o[c] (own pixel, chunk cbase + c) -> f[k] (pixel 2g + k, chunk cbase + j2)
         uint32_t f[2][8];
@@ -332,8 +347,8 @@ bool conv_stack_tc_supported(int Cin, int Cout) {
 }
 
 // x (N,H,W,Cin) bf16, w_packed [64][9][Cin] bf16 (FOSVOS_W_TC_FWD / _DGRAD), y / mask (N,H,W,64) bf16, y_pool pooled.
-int conv_stack_tc_launch(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, int N, int H,
-                         int W, int Cin, int relu, cudaStream_t stream) {
+int conv_stack_tc_launch(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, void* pool_arg,
+                         int N, int H, int W, int Cin, int relu, cudaStream_t stream) {
   SkEncodeTiledFn enc = sk_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FOSVOS_ERR_DRIVER; }
   SkParams p;
@@ -341,6 +356,7 @@ int conv_stack_tc_launch(const void* x, const void* w_packed, const float* bias,
   p.mask = (const __nv_bfloat16*)mask;
   p.y = (__nv_bfloat16*)y;
   p.y_pool = (__nv_bfloat16*)y_pool;
+  p.pool_arg = (uint32_t*)pool_arg;
   p.relu = relu;
   p.N = N; p.H = H; p.W = W;
   p.tiles_x = ceil_div(W, SK_OUT_W);

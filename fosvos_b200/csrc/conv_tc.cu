@@ -50,8 +50,8 @@ namespace fosvos {
 
 // conv_stack_tc.cu
 bool conv_stack_tc_supported(int Cin, int Cout);
-int conv_stack_tc_launch(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, int N, int H,
-                         int W, int Cin, int relu, cudaStream_t stream);
+int conv_stack_tc_launch(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, void* pool_arg,
+                         int N, int H, int W, int Cin, int relu, cudaStream_t stream);
 
 constexpr int TC_BM = 128;       // pixels per tile
 constexpr int TC_BK = 64;        // channels per K slab (128 B of bf16 = one swizzle row)
@@ -111,6 +111,8 @@ struct TcParams {
   const __nv_bfloat16* mask;     // (N,H,W,CoutP) or null
   __nv_bfloat16* y;              // (N,H,W,CoutP)
   __nv_bfloat16* y_pool;         // (N,ceil(H/2),ceil(W/2),CoutP) or null: 2x2/2 ceil-mode max pool of y, fused (ReLU outputs only)
+  uint32_t* pool_arg;            // (N,ceil(H/2),ceil(W/2),CoutP/32,2) or null: 2-bit window index of the (first) maximum per pooled
+                                 // element, as two bit planes per 32 channels {bit 0, bit 1}; index = 2 dy + dx in scan order
   const __nv_bfloat16* w;        // packed weight (MODE_C8 reads it directly)
   int N, H, W, CoutP;
   int tiles_x, tiles_y, n_tiles_n, total_tiles;
@@ -604,7 +606,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               // nn.MaxPool2d(2, 2, ceil_mode=True) on the way out (osvos_vgg.py:90).  A warp holds whole image rows of
               // the patch, so the 2x2 partners are lanes +1 and +TW.  Out-of-frame pixels count as 0: the values are
               // post-ReLU, so a zero never wins against an in-frame value and ceil-mode windows come out right.
+              // With `pool_arg` the window index of the maximum is recorded too (what max_pool2d_with_indices keeps: the FIRST
+              // maximum in scan order, i.e. a later candidate wins only if strictly greater; non-negative bf16 compare as
+              // integers), so the pool's backward pass never re-reads the full-resolution activation.
               uint32_t m[16];
+              uint32_t right_wins = 0u, row2_wins = 0u;        // bit 2 i + h: channel 2 i + h of this thread's 32
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const uint32_t mine = in_img ? packed[i] : 0u;
@@ -614,6 +620,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 const uint32_t below = __shfl_down_sync(0xffffffffu, am, TW);
                 __nv_bfloat162 b = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(&below));
                 m[i] = *reinterpret_cast<uint32_t*>(&b);
+                if (p.pool_arg) {
+                  right_wins |= ((right & 0xffffu) > (mine & 0xffffu) ? 1u : 0u) << (2 * i) | ((right >> 16) > (mine >> 16) ? 1u : 0u) << (2 * i + 1);
+                  row2_wins |= ((below & 0xffffu) > (am & 0xffffu) ? 1u : 0u) << (2 * i) | ((below >> 16) > (am >> 16) ? 1u : 0u) << (2 * i + 1);
+                }
+              }
+              if (p.pool_arg) {
+                const uint32_t right_wins_below = __shfl_down_sync(0xffffffffu, right_wins, TW);
+                if (in_img && !(px & 1) && !(py & 1) && co0 + 32 * half < p.CoutP) {
+                  const int PH = (p.H + 1) >> 1, PW = (p.W + 1) >> 1;
+                  uint32_t* dst = p.pool_arg + ((((long long)n * PH + (gy >> 1)) * PW + (gx >> 1)) * (p.CoutP >> 5) + ((co0 + 32 * half) >> 5)) * 2;
+                  *reinterpret_cast<uint2*>(dst) = make_uint2((row2_wins & right_wins_below) | (~row2_wins & right_wins), row2_wins);
+                }
               }
               if (in_img && !(px & 1) && !(py & 1)) {
                 const int PH = (p.H + 1) >> 1, PW = (p.W + 1) >> 1;
@@ -848,7 +866,7 @@ struct TcSplit {
 
 static int conv_tc_common(const void* x, const void* w_packed, const float* bias, const void* mask, void* y, void* y_pool, int N,
                           int H, int W, int Cin, int Cout, int taps, int flags, fosvos_stream_t stream, const char* what,
-                          const TcSplit* split = nullptr) {
+                          const TcSplit* split = nullptr, void* pool_arg = nullptr) {
   FOSVOS_REQUIRE(x && w_packed && (y || y_pool || (split && split->y_f32)) && N > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", what);
   FOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin > 0 && Cout > 0,
                  "%s: Cin=%d and Cout=%d must be positive multiples of 8 (pad the NHWC tensors)", what, Cin, Cout);
@@ -864,13 +882,14 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
       (!(flags & FOSVOS_CONV_MASK) || Cin >= 128 || getenv("FOSVOS_TC_STACK_ALL")) &&
       !((flags & FOSVOS_CONV_MASK) && (flags & FOSVOS_CONV_RELU)) && (((uintptr_t)mask | (uintptr_t)y | (uintptr_t)y_pool) & 31) == 0 &&      // its epilogue moves 32 bytes per access
       !getenv("FOSVOS_TC_NO_STACK"))
-    return conv_stack_tc_launch(x, w_packed, (flags & FOSVOS_CONV_BIAS) ? bias : nullptr, (flags & FOSVOS_CONV_MASK) ? mask : nullptr, y, y_pool, N,
-                                H, W, Cin, (flags & FOSVOS_CONV_RELU) ? 1 : 0, as_stream(stream));
+    return conv_stack_tc_launch(x, w_packed, (flags & FOSVOS_CONV_BIAS) ? bias : nullptr, (flags & FOSVOS_CONV_MASK) ? mask : nullptr, y, y_pool,
+                                pool_arg, N, H, W, Cin, (flags & FOSVOS_CONV_RELU) ? 1 : 0, as_stream(stream));
   TcParams p;
   p.bias = bias;
   p.mask = (const __nv_bfloat16*)mask;
   p.y = (__nv_bfloat16*)y;
   p.y_pool = (__nv_bfloat16*)y_pool;
+  p.pool_arg = (uint32_t*)pool_arg;
   p.w = (const __nv_bfloat16*)w_packed;
   p.N = N; p.H = H; p.W = W; p.CoutP = Cout;
   p.seg_len = split ? split->seg_len : 0;
@@ -1028,6 +1047,16 @@ int fosvos_conv3x3_tc_pool(const void* x, const void* w_packed, const float* bia
                  "conv3x3_tc_pool: the fused pool needs the RELU epilogue (non-negative values) and no mask/accumulate");
   FOSVOS_REQUIRE(Cout >= 64 && ((uintptr_t)y_pool & 15) == 0, "conv3x3_tc_pool: Cout=%d must be >= 64 (slab epilogue), y_pool 16-byte aligned", Cout);
   return conv_tc_common(x, w_packed, bias, nullptr, y, y_pool, N, H, W, Cin, Cout, 9, flags, stream, "conv3x3_tc_pool");
+}
+
+int fosvos_conv3x3_tc_pool_arg(const void* x, const void* w_packed, const float* bias, void* y, void* y_pool, void* pool_arg, int N, int H,
+                               int W, int Cin, int Cout, int flags, fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(y_pool && pool_arg, "conv3x3_tc_pool_arg: y_pool or pool_arg is null");
+  FOSVOS_REQUIRE((flags & FOSVOS_CONV_RELU) && !(flags & (FOSVOS_CONV_MASK | FOSVOS_CONV_ACCUMULATE)),
+                 "conv3x3_tc_pool_arg: the fused pool needs the RELU epilogue (non-negative values) and no mask/accumulate");
+  FOSVOS_REQUIRE(Cout >= 64 && Cout % 32 == 0 && ((uintptr_t)y_pool & 15) == 0 && ((uintptr_t)pool_arg & 7) == 0,
+                 "conv3x3_tc_pool_arg: Cout=%d must be a multiple of 32 and >= 64, y_pool 16-byte and pool_arg 8-byte aligned", Cout);
+  return conv_tc_common(x, w_packed, bias, nullptr, y, y_pool, N, H, W, Cin, Cout, 9, flags, stream, "conv3x3_tc_pool_arg", nullptr, pool_arg);
 }
 
 }  // extern "C"

@@ -87,6 +87,43 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
   }
 }
 
+// The same with the window index of the maximum already known (two bit planes per 32 channels, written by the fused
+// conv + pool epilogues: fosvos_conv3x3_tc_pool_arg): the full-resolution activation is not read at all.
+template <typename T, typename IDX>
+__global__ void maxpool_bwd_arg_kernel(const uint32_t* __restrict__ arg, const T* __restrict__ dy, const T* add, T* dx, int H,
+                                       int W, int C, int OH, int OW, long long total) {
+  const IDX groups = (IDX)(C / 8);
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < (IDX)total; i += (IDX)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    IDX r = i / groups;
+    const long long opix = (long long)r;               // ((n * OH + oy) * OW + ox)
+    const int ox = (int)(r % (IDX)OW); r /= (IDX)OW;
+    const int oy = (int)(r % (IDX)OH);
+    const long long n = (long long)(r / (IDX)OH);
+    const uint2 planes = __ldg(reinterpret_cast<const uint2*>(arg + (opix * (C >> 5) + (g >> 2)) * 2));
+    const int sh = (g & 3) * 8;
+    const uint32_t lo = planes.x >> sh, hi = planes.y >> sh;
+    float gsrc[8];
+    load8(dy + opix * C + g * 8, gsrc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int iy = 2 * oy + (k >> 1), ix = 2 * ox + (k & 1);
+      if (iy < H && ix < W) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (int)(((lo >> j) & 1u) | (((hi >> j) & 1u) << 1)) == k ? gsrc[j] : 0.f;
+        if (add) {                                    // gradient fan-in: the other consumer's contribution (may alias dx)
+          float a[8];
+          load8(add + ((n * H + iy) * W + ix) * C + g * 8, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        store8(dx + ((n * H + iy) * W + ix) * C + g * 8, o);
+      }
+    }
+  }
+}
+
 }  // namespace fosvos
 
 using namespace fosvos;
@@ -125,6 +162,22 @@ int fosvos_maxpool2x2_bwd_add(const void* x, const void* dy, const void* add, vo
       maxpool_bwd_kernel<T, long long><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)dy, (const T*)add, (T*)dx, H, W, C, OH, OW, total);
   });
   return check_launch("maxpool2x2_bwd");
+}
+
+int fosvos_maxpool2x2_bwd_arg(const void* pool_arg, const void* dy, const void* add, void* dx, int N, int H, int W, int C, int dtype,
+                              fosvos_stream_t stream) {
+  FOSVOS_REQUIRE(pool_arg && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0 && ((uintptr_t)pool_arg & 7) == 0,
+                 "maxpool2x2_bwd_arg: bad arguments (C=%d must be a multiple of 32, the index map 8-byte aligned)", C);
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  const int blocks = (int)min((long long)num_sms() * 16, ceil_div_ll(total, 256));
+  FOSVOS_DISPATCH_DTYPE(dtype, T, {
+    if (total + (long long)blocks * 256 < (1LL << 32))
+      maxpool_bwd_arg_kernel<T, unsigned><<<blocks, 256, 0, as_stream(stream)>>>((const uint32_t*)pool_arg, (const T*)dy, (const T*)add, (T*)dx, H, W, C, OH, OW, total);
+    else
+      maxpool_bwd_arg_kernel<T, long long><<<blocks, 256, 0, as_stream(stream)>>>((const uint32_t*)pool_arg, (const T*)dy, (const T*)add, (T*)dx, H, W, C, OH, OW, total);
+  });
+  return check_launch("maxpool2x2_bwd_arg");
 }
 
 }  // extern "C"

@@ -75,6 +75,11 @@ class OSVOS_VGG(nn.Module):
         self.precision = os.environ.get("FOSVOS_PRECISION", "bf16")       # (property: also turns the leaves into fosvos_b200.leaf classes)
         self.introspect = False                                            # True: always run module by module (hooks fire), see leaf.py
         self.fuse_pool = os.environ.get("FOSVOS_FUSE_POOL", "1") != "0"    # max pool written by the producing conv's epilogue
+        # training: the fused pool also records the window index of every maximum (what autograd keeps for MaxPool2d's
+        # backward), so the pool gradient never re-reads the full-resolution activation -- and conv1_2's output, which only
+        # the pool consumes (stage 0 has no side output, osvos_vgg.py:63,68), is not written at all
+        self.pool_arg = os.environ.get("FOSVOS_POOL_ARG", "1") != "0"
+        self._keep_activations = False      # set by consumers that read every conv's output (prune.py: Taylor ranks)
         # side_prep through the row-stacked tcgen05 kernel with the 1x1 heads fused into its epilogue (conv_side_tc.cu)
         self.side_tc = os.environ.get("FOSVOS_SIDE_TC", "1") != "0"
         # side_prep convs and weight gradients are off the critical dependency chain: issue them on a second stream so
@@ -317,14 +322,17 @@ class OSVOS_VGG(nn.Module):
         conv_in: List[torch.Tensor] = []        # input activation of every stage conv, in order
         conv_out: List[torch.Tensor] = []
         pool_in: List[Optional[torch.Tensor]] = []
+        pool_arg: List[Optional[torch.Tensor]] = []        # per pool: recorded window indices (training, fused pool) or None
+        arg: Optional[torch.Tensor] = None
         stage_out: List[torch.Tensor] = []
         sps: List[torch.Tensor] = []
         pooled: Optional[torch.Tensor] = None   # the next stage's input when the pool rode along in the conv epilogue
         for si, convs in enumerate(self._stage_convs()):
             if si > 0:
                 pool_in.append(a)
+                pool_arg.append(arg)
                 a = pooled if pooled is not None else ops.maxpool2x2(a)
-                pooled = None
+                pooled = arg = None
             for ci, conv in enumerate(convs):
                 pc = self._packed_for(conv, need_dgrad=save)
                 conv_in.append(a)
@@ -335,6 +343,9 @@ class OSVOS_VGG(nn.Module):
                         # its 52 MB/frame full-resolution map is never written
                         pooled = ops.conv3x3_pool_only(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU)
                         a = None
+                    elif save and getattr(self, "pool_arg", True) and cp % 32 == 0:
+                        a, pooled, arg = ops.conv3x3_pool_arg(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU,
+                                                              want_y=si > 0 or getattr(self, "_keep_activations", False))
                     else:
                         a, pooled = ops.conv3x3_pool(a, pc.w_fwd, pc.bias, cp, L.CONV_BIAS | L.CONV_RELU)
                 else:
@@ -372,7 +383,7 @@ class OSVOS_VGG(nn.Module):
             outs, prob, mask = ops.side_fwd(sps, params, H, W, general=mode, want_prob=want_prob, want_mask=want_mask)
         saved = None
         if save:
-            saved = dict(conv_in=conv_in, conv_out=conv_out, pool_in=pool_in, stage_out=stage_out, sps=sps, H=H, W=W,
+            saved = dict(conv_in=conv_in, conv_out=conv_out, pool_in=pool_in, pool_arg=pool_arg, stage_out=stage_out, sps=sps, H=H, W=W,
                          params=params)
         return outs, prob, mask, saved
 
@@ -480,6 +491,8 @@ class OSVOS_VGG(nn.Module):
                 name = names[si][j]
                 wgrad(name, x_in, dz)
                 if taylor is not None and name in taylor:
+                    if saved["conv_out"][k] is None:
+                        raise RuntimeError("fosvos_b200: Taylor ranks need every conv's output: run the forward pass with net._keep_activations = True")
                     ops.taylor_rank(saved["conv_out"][k], dz, taylor[name])
                 if si == 0 and j == 0:
                     break
@@ -491,10 +504,23 @@ class OSVOS_VGG(nn.Module):
             if si > 0:
                 if si - 1 > 0 and side_done[si - 1] is not None:
                     main.wait_event(side_done[si - 1])
-                dA = ops.maxpool2x2_bwd(saved["pool_in"][si - 1], dz, add=dA_side[si - 1])
+                arg = saved.get("pool_arg", [None] * 4)[si - 1]
+                if arg is not None:
+                    hh, ww = self._pool_input_hw(saved, si - 1)
+                    dA = ops.maxpool2x2_bwd_arg(arg, dz, hh, ww, add=dA_side[si - 1])
+                else:
+                    dA = ops.maxpool2x2_bwd(saved["pool_in"][si - 1], dz, add=dA_side[si - 1])
         if aux is not None:
             main.wait_stream(aux)
         keep.clear()
+
+    @staticmethod
+    def _pool_input_hw(saved, pool_index: int):
+        """(height, width) of the input of pool ``pool_index`` (0 = after stage 0): ceil-mode halvings of the frame size."""
+        h, w = saved["H"], saved["W"]
+        for _ in range(pool_index):
+            h, w = (h + 1) // 2, (w + 1) // 2
+        return h, w
 
     def _grad_names(self) -> List[str]:
         return [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("upscale")]

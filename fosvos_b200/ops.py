@@ -98,6 +98,38 @@ def conv3x3_pool(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
     return y, yp
 
 
+def conv3x3_pool_arg(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout_p: int, flags: int,
+                     want_y: bool = True):
+    """Training form of the fused pool: (y or None, pooled, arg) -- ``arg`` (N, PH, PW, cout_p / 32, 2) int32 holds the window
+    index of each pooled element's (first) maximum as two bit planes per 32 channels, which ``maxpool2x2_bwd_arg`` consumes
+    instead of re-reading ``y``.  ``want_y=False``: the full-resolution map is not written at all."""
+    L.require_device(x.device)
+    n, h, w, cin_p = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and cout_p % 32 == 0
+    ph, pw = (h + 1) // 2, (w + 1) // 2
+    y = torch.empty((n, h, w, cout_p), dtype=x.dtype, device=x.device) if want_y else None
+    yp = torch.empty((n, ph, pw, cout_p), dtype=x.dtype, device=x.device)
+    arg = torch.empty((n, ph, pw, cout_p // 32, 2), dtype=torch.int32, device=x.device)
+    L.check(L.lib().fosvos_conv3x3_tc_pool_arg(x.data_ptr(), w_packed.data_ptr(), L.ptr(bias), L.ptr(y), yp.data_ptr(), arg.data_ptr(),
+                                               n, h, w, cin_p, cout_p, flags, L.stream()), "conv3x3_tc_pool_arg")
+    return y, yp, arg
+
+
+def maxpool2x2_bwd_arg(arg: torch.Tensor, dy: torch.Tensor, h: int, w: int, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradient of the pool w.r.t. its (n, h, w, c) input from the recorded window indices; with ``add`` the result is
+    written INTO it (fan-in, as ``maxpool2x2_bwd``)."""
+    L.require_device(dy.device)
+    n, ph, pw, c = dy.shape
+    assert (ph, pw) == ((h + 1) // 2, (w + 1) // 2) and c % 32 == 0 and dy.is_contiguous()
+    assert arg.dtype == torch.int32 and arg.shape == (n, ph, pw, c // 32, 2) and arg.is_contiguous()
+    if add is not None:
+        assert add.shape == (n, h, w, c) and add.dtype == dy.dtype and add.is_contiguous()
+    dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device) if add is None else add
+    L.check(L.lib().fosvos_maxpool2x2_bwd_arg(arg.data_ptr(), dy.data_ptr(), L.ptr(add), dx.data_ptr(), n, h, w, c,
+                                              L.dtype_code(dy.dtype), L.stream()), "maxpool2x2_bwd_arg")
+    return dx
+
+
 def conv3x3_pool_only(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout_p: int, flags: int) -> torch.Tensor:
     """Same launch with the full-resolution output suppressed: only the pooled map leaves the kernel (inference, when
     nothing but the pool consumes the conv -- conv1_2, osvos_vgg.py:63,68)."""
@@ -662,7 +694,7 @@ def mask_iou(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # every launching wrapper runs with its tensors' device current (see _lib.on_tensor_device)
-for _name in ("nchw_to_nhwc", "nhwc_to_nchw", "pack_weight", "pad_bias", "split_frames", "pack_weight_split", "conv3x3_split", "maxpool2x2_split", "conv3x3", "conv3x3_pool", "conv3x3_pool_only", "conv3x3_side",
+for _name in ("nchw_to_nhwc", "nhwc_to_nchw", "pack_weight", "pad_bias", "split_frames", "pack_weight_split", "conv3x3_split", "maxpool2x2_split", "conv3x3", "conv3x3_pool", "conv3x3_pool_only", "conv3x3_pool_arg", "maxpool2x2_bwd_arg", "conv3x3_side",
               "conv3x3_wgrad_accumulate", "conv3x3_wgrad_finish", "conv3x3_wgrad", "maxpool2x2", "maxpool2x2_bwd", "side_params_prepare",
               "side_check_diagonal", "side_fwd", "side_fwd_heads_done", "side_bwd", "bal_loss_fwd", "bal_loss_fwd_bwd",
               "bal_loss_fwd_bwd_frames", "bal_loss_bwd", "loss_accumulate", "loss_window_finish", "wgrad_fold_all", "repack_all", "sgd_step", "adam_step", "pixel_loss", "taylor_rank", "relu_fwd", "relu_bwd",

@@ -60,7 +60,11 @@ class FilterPruner:
                 self.filter_ranks[k] = torch.zeros(net.stages[si][mi].out_channels, dtype=torch.float32, device=dev)
             taylor[name] = self.filter_ranks[k]
         with torch.no_grad():
-            outs, _, _, saved = net._run_forward(x, save=True)
+            keep, net._keep_activations = net._keep_activations, True      # the ranks read every conv's output, conv1_2's included
+            try:
+                outs, _, _, saved = net._run_forward(x, save=True)
+            finally:
+                net._keep_activations = keep
             douts: List[Optional[torch.Tensor]] = [None] * 5
             total = None
             for i in (range(5) if is_offline else [4]):

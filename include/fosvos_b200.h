@@ -118,6 +118,13 @@ int fosvos_conv3x3_tc_pool(const void* x, const void* w_packed, const float* bia
                            fosvos_stream_t stream);
 /* (y may be NULL: only the pooled map is written -- inference never reads the full-resolution
  * output of a stage's last conv when nothing else consumes it, e.g. conv1_2, osvos_vgg.py:63,68.) */
+/* Training form: additionally records WHICH element of each 2x2 window the maximum is -- the index
+ * autograd's max_pool2d_with_indices keeps for nn.MaxPool2d's backward (osvos_vgg.py:90): the first maximum
+ * in (row, col) scan order, 2 dy + dx.  pool_arg: (N,ceil(H/2),ceil(W/2),Cout/32,2) uint32, two bit planes
+ * {bit 0, bit 1} per 32 channels (bit c % 32 = channel c).  Cout % 32 == 0.  fosvos_maxpool2x2_bwd_arg consumes it. */
+int fosvos_conv3x3_tc_pool_arg(const void* x, const void* w_packed, const float* bias, void* y,
+                               void* y_pool, void* pool_arg, int N, int H, int W, int Cin, int Cout,
+                               int flags, fosvos_stream_t stream);
 
 /* side_prep: nn.Conv2d(C, 16, 3, padding=1) with bias and NO ReLU (osvos_vgg.py:42,69) on the tensor
  * cores with the three taps of a kernel row stacked along GEMM-N (N = 48; conv_side_tc.cu).
@@ -192,6 +199,10 @@ int fosvos_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H,
 /* Same with gradient fan-in: dx = add + pool gradient (add: same shape as dx, may alias it, may be NULL). */
 int fosvos_maxpool2x2_bwd_add(const void* x, const void* dy, const void* add, void* dx, int N, int H,
                               int W, int C, int dtype, fosvos_stream_t stream);
+/* Same from the recorded window indices (fosvos_conv3x3_tc_pool_arg) instead of the pool's input: the
+ * full-resolution activation is not read.  C % 32 == 0. */
+int fosvos_maxpool2x2_bwd_arg(const void* pool_arg, const void* dy, const void* add, void* dx, int N,
+                              int H, int W, int C, int dtype, fosvos_stream_t stream);
 
 /* ---- side-output chain (osvos_vgg.py:69-82) -------------------------------------------
  * score_dsn 1x1 (:75) -> upscale_ ConvT (:76) -> crop (:77) for the four side maps, and

@@ -255,6 +255,49 @@ def test_conv3x3_row_stack_dgrad(case, monkeypatch):
     assert (got[_bf16r(xprev) <= 0] == 0).all()
 
 
+def _window_argmax(y):
+    """(n, h, w, c) non-negative map -> (n, ph, pw, c) index 2 dy + dx of the FIRST maximum of each 2x2 ceil-mode window"""
+    n, h, w_, c = y.shape
+    ph, pw = (h + 1) // 2, (w_ + 1) // 2
+    pad = torch.full((n, 2 * ph, 2 * pw, c), -1.0, device=y.device)
+    pad[:, :h, :w_] = y.float()
+    cand = torch.stack([pad[:, 0::2, 0::2], pad[:, 0::2, 1::2], pad[:, 1::2, 0::2], pad[:, 1::2, 1::2]], dim=-1)
+    return cand.argmax(dim=-1)
+
+
+def _unpack_arg(arg, c):
+    """(n, ph, pw, c / 32, 2) int32 bit planes -> (n, ph, pw, c) indices"""
+    bits = torch.arange(32, device=arg.device)
+    lo = (arg[..., 0].unsqueeze(-1) >> bits) & 1
+    hi = (arg[..., 1].unsqueeze(-1) >> bits) & 1
+    return (lo + 2 * hi).reshape(*arg.shape[:3], c)
+
+
+@pytest.mark.parametrize("case", [(1, 33, 45, 64, 64), (2, 16, 28, 64, 64), (2, 16, 24, 64, 128), (1, 31, 70, 128, 256), (1, 9, 13, 128, 64),
+                                  (1, 1, 1, 64, 64), (1, 7, 30, 256, 512)])
+def test_conv3x3_pool_arg_and_backward(case):
+    """Training form of the fused pool (both tensor-core kernels): same y / pooled map as the plain fused pool, window indices
+    = the first maximum in scan order (sparse post-ReLU maps: many ties at zero), and the pool gradient routed by those
+    indices == the one found by re-reading the activation, with and without fan-in."""
+    n, h, w_, cin, cout = case
+    g = _gen(71)
+    x = _nhwc(torch.randn(n, cin, h, w_, generator=g), torch.bfloat16)
+    wp = ops.pack_weight(torch.randn(cout, cin, 3, 3, generator=g).to(DEV) * 0.05, L.W_TC_FWD, torch.bfloat16)
+    bp = ops.pad_bias(torch.randn(cout, generator=g).to(DEV) - 0.5, cout, DEV)          # negative shift: ~70 % zeros after ReLU
+    fl = L.CONV_BIAS | L.CONV_RELU
+    y_ref, p_ref = ops.conv3x3_pool(x, wp, bp, cout, fl)
+    y, yp, arg = ops.conv3x3_pool_arg(x, wp, bp, cout, fl)
+    assert torch.equal(y, y_ref) and torch.equal(yp, p_ref)
+    y0, yp0, arg0 = ops.conv3x3_pool_arg(x, wp, bp, cout, fl, want_y=False)
+    assert y0 is None and torch.equal(yp0, p_ref) and torch.equal(arg0, arg)
+    assert torch.equal(_unpack_arg(arg, cout), _window_argmax(y_ref))
+    dy = _nhwc(torch.randn(n, cout, (h + 1) // 2, (w_ + 1) // 2, generator=g), torch.bfloat16)
+    assert torch.equal(ops.maxpool2x2_bwd_arg(arg, dy, h, w_), ops.maxpool2x2_bwd(y_ref, dy))
+    add = _nhwc(torch.randn(n, cout, h, w_, generator=g), torch.bfloat16)
+    a1, a2 = add.clone(), add.clone()
+    assert torch.equal(ops.maxpool2x2_bwd_arg(arg, dy, h, w_, add=a1), ops.maxpool2x2_bwd(y_ref, dy, add=a2))
+
+
 SIDE_CASES = [
     # N, H, W, Cin: tile = 30 x 4 outputs; widths around the tile edge, one-pixel maps, ragged channel counts (pruned nets)
     (1, 30, 54, 512), (2, 15, 27, 512), (1, 45, 70, 128), (3, 7, 5, 64), (1, 4, 30, 256), (1, 5, 31, 128), (1, 3, 29, 64),
