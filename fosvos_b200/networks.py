@@ -466,7 +466,11 @@ class OSVOS_VGG(nn.Module):
                     side_done[si].record(aux)
             wgrad(f"side_prep.{si - 1}", a_out, dsp[si - 1])
 
-        fanin_pool = os.environ.get("FOSVOS_BWD_FANIN", "epilogue") == "pool"
+        # where the two gradients of a stage output meet: "pool" (default) = the side_prep data gradient is written on its own
+        # (off the main chain, on the auxiliary stream) and the pool's backward adds it while routing (coalesced 16-byte reads);
+        # "epilogue" = the side_prep data gradient's epilogue accumulates into the pool gradient (a per-pixel read-modify-write:
+        # 32 lines per warp instruction).  Measured on the sequence job: 0.4156 against 0.4221 s of fine-tune per sequence.
+        fanin_pool = os.environ.get("FOSVOS_BWD_FANIN", "pool") == "pool"
         if fanin_pool:
             side_branch(4, on_aux=False)
         dA: Optional[torch.Tensor] = None          # gradient w.r.t. the current stage's output (pre-activation-masked)

@@ -125,7 +125,11 @@ def test_forward_pruned_golden():
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["fwd_48x72_random", "fwd_45x70_random"])
-def test_backward_golden(name, precision):
+@pytest.mark.parametrize("fanin", ["pool", "epilogue"])
+def test_backward_golden(name, precision, fanin, monkeypatch):
+    # both places where the two gradients of a stage output can meet (FOSVOS_BWD_FANIN: the pool's backward adds the
+    # side_prep branch -- the default -- or the side_prep data gradient's epilogue accumulates into the pool gradient)
+    monkeypatch.setenv("FOSVOS_BWD_FANIN", fanin)
     fix = _load(name + ".pt")
     x, m, sd = _case(fix)
     net = _net(sd, precision)
