@@ -390,7 +390,7 @@ def conv_roofline(net, frames, peaks, precision):
         tj = json.load(open(tp))
         if tj.get("batch") == n:
             traffic, traffic_src = tj["traffic_bytes"], "profiles/r02_conv_forward_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the 17 launches of one batch-%d forward)" % n
-    return dict(bound="tensor", kernel="conv3x3_tc_kernel + conv3x3_side_tc_kernel (17 launches = one inference forward pass)" if tc else "conv3x3_simt_kernel",
+    return dict(bound="tensor", kernel="conv3x3_tc_kernel + conv3x3_stack_tc_kernel (conv1_2) + conv3x3_side_tc_kernel (17 launches = one inference forward pass)" if tc else "conv3x3_simt_kernel",
                 achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
                 peak_source=peaks["source"] + " burst", batch=n, gflop_per_frame=gflop / n, ms_per_forward_convs=ms, per_layer=per_layer)
 
@@ -433,8 +433,8 @@ def backward_rooflines(net, frames, peaks, n_window):
                 o = torch.empty_like(x)
                 dg.append((lambda x=x, dz=dz, pc=pc, o=o: ops.conv3x3(dz, pc.w_dgrad, None, x.shape[3], L.CONV_MASK, mask=x, out=o), sp_conv, x.shape[1], x.shape[2]))
         out = []
-        for name, plan in (("conv3x3_wgrad_tc_kernel (17 launches = the weight gradients of one window)", wg),
-                           ("conv3x3_tc_kernel, data-gradient use (16 launches = the data gradients of one window)", dg)):
+        for name, plan in (("conv3x3_wgrad_tc_kernel + conv3x3_wgrad_tc_pair_kernel (17 launches = the weight gradients of one window)", wg),
+                           ("conv3x3_tc_kernel / conv3x3_stack_tc_kernel, data-gradient use (16 launches = the data gradients of one window)", dg)):
             ms = _time_ms(lambda: [fn() for fn, *_ in plan], reps=3)
             gflop = sum(_conv_flops(c, h, w, n) for _, c, h, w in plan)
             per_layer = [dict(cin=c.in_channels, cout=c.out_channels, hw=[h, w], ms=round(_time_ms(fn, reps=3), 4)) for fn, c, h, w in plan]
