@@ -74,6 +74,7 @@ struct WgParams {
   int one_pass;              // Cin == Cout == 64: A = X under two column shifts, B = dZ under three row shifts, all taps per visit
   int zstack;                // X on M, dZ (<= 64 channels) as ONE halo box whose three row shifts are one N = 192 MMA (one_pass, side_prep)
   int c8_lbo, c8_sbo;        // descriptor strides of its un-swizzled X operand (160 / 16)
+  int c8_rows3;              // first layer: the three kernel rows in one N = 184 MMA
   int debug;                 // FOSVOS_WG_DEBUG (timing experiments only): 1 = skip the reductions, 2 = no start rotation, 3 = no MMAs, 4 = no loads, 5 = neither, 6 = 5 + 1
 };
 
@@ -224,6 +225,18 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const uint32_t a_base = st, b_base = st + p.a_bytes;
         if (p.c8) {
           if (ptx::elect_one()) {
+            if (p.c8_rows3) {
+              // all nine taps in ONE MMA per 16 pixels: the 8-channel blocks of B are 16 B apart along N, and a halo row is
+              // 10 blocks long, so block 10 r + s is tap (r, s): N = 8 * 23 = 184 (92 cycles) instead of three N = 32
+              // MMAs (3 x 40); the blocks in between multiply pixels further right and are never stored
+              const uint32_t idesc184 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(184 >> 3) << 17);
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t da = umma_desc_sw128_mnmajor(a_base + kk * 2048, WG_PLAIN_BLOCK);
+                const uint64_t db = umma_desc_noswizzle_mnmajor(b_base + 2 * kk * WG_C8_ROW, p.c8_lbo, p.c8_sbo);
+                ptx::umma_bf16(tmem_base, da, db, idesc184, (pt != p_begin) || (kk != 0));
+              }
+            } else {
 #pragma unroll 1
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -233,6 +246,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 const uint64_t db = umma_desc_noswizzle_mnmajor(b_base + (r + 2 * kk) * WG_C8_ROW, p.c8_lbo, p.c8_sbo);
                 ptx::umma_bf16(tmem_base + r * p.n_cols, da, db, idesc, (pt != p_begin) || (kk != 0));
               }
+            }
             }
             ptx::umma_commit(&empty_bar[stage]);
             if (pt == p_end - 1) ptx::umma_commit(done_bar);
@@ -330,7 +344,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         // accumulator r, column block sc = tap (r, sc), 8 channels each: ws[tap][cout][8]
 #pragma unroll 1
         for (int r = 0; r < 3; ++r) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * p.n_cols;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * (p.c8_rows3 ? 80 : p.n_cols);
 #pragma unroll 1
           for (int c0 = 0; c0 < 32; c0 += 16) {
             uint32_t v[16];
@@ -740,6 +754,7 @@ int fosvos_conv3x3_wgrad_tc_accumulate(const void* x, const void* dz, float* db,
   static const bool side_one_pass = getenv("FOSVOS_WG_SIDE_THREE_PASSES") == nullptr;
   p.one_pass = (p.x_is_a && !no_stack && ((CinP == 64 && CoutP == 64) || (side_one_pass && CoutP <= 64 && CoutP % 4 == 0))) ? 1 : 0;
   p.c8_lbo = WG_C8_ROW; p.c8_sbo = 16;
+  p.c8_rows3 = (p.c8 && !getenv("FOSVOS_WG_C8_THREE_MMAS")) ? 1 : 0;
   p.n_cols = p.c8 ? 32 : p.Ntot >= 128 ? 128 : (p.Ntot > 16 ? 64 : 16);
   p.nb_n = (p.n_cols + 63) / 64;
   p.stack = (!p.x_is_a && !p.c8 && p.Ntot == 64 && !no_stack) ? 1 : 0;
