@@ -2,8 +2,9 @@
 // three taps of a kernel ROW stacked along GEMM-N, and optionally the two 1x1 heads of the side chain (score_dsn,
 // osvos_vgg.py:75, and this stage's 16 columns of fuse, :81) applied in the epilogue.
 //
-// Why not the generic kernel (conv_tc.cu, N = 16): one M = 128 tcgen05.mma costs max(N / 2, ~57) cycles, so with N = 16
-// every one of the 9 * Cin / 16 instructions of a tile pays the ~57-cycle floor (12 % tensor pipe, ncu r01i).  Here
+// Why not the generic kernel (conv_tc.cu, N = 16): one M = 128 tcgen05.mma costs max(N / 2, 32 + N / 4) cycles -- reading the
+// 128-row A tile alone takes 32 (tools/exp/mma_side.cu; ~57 per instruction in the round-1 kernel) -- so with N = 16 every one
+// of the 9 * Cin / 16 instructions of a tile pays that floor for 8 cycles of tensor work (12 % tensor pipe, ncu r01i).  Here
 //
 //   D[q, (s, co)] = sum_r sum_c X[q + (r - 1, 0), c] * W[co, r, s, c]           one GEMM, N = 3 * 16 = 48, K = 3 * Cin
 //   out[y, x, co] = b[co] + D[(y, x - 1), (0, co)] + D[(y, x), (1, co)] + D[(y, x + 1), (2, co)]

@@ -924,7 +924,8 @@ static int conv_tc_common(const void* x, const void* w_packed, const float* bias
   if (getenv("FOSVOS_TC_SKIP_B")) p.flags |= TC_FLAG_SKIP_B;
   if (getenv("FOSVOS_TC_SKIP_A")) p.flags |= TC_FLAG_SKIP_A;
   const long long m_tiles = (long long)N * p.tiles_x * p.tiles_y;
-  // N tile: minimise waves x cycles per tile.  One M=128 tcgen05.mma costs max(N/2, ~57) cycles
+  // N tile: minimise waves x cycles per tile.  One M=128 tcgen05.mma costs max(N/2, 32 + N/4) cycles with resident operands
+  // (tools/exp/mma_side.cu); in this kernel a narrow one was measured at ~57 (round 1), the constant kept below
   // (tools/exp/mma_issue.cu), so tiles narrower than 128 only pay when they fill an otherwise idle machine.
   int BN = 16;
   {

@@ -22,17 +22,19 @@
 // the frame is described to TMA as (8 W, H, N), so ONE 160 B x 18-row halo box per 16 x 8 patch serves all nine
 // taps: tap (r, s) is the same tile read from byte offset r * 160 + s * 16.  With SBO = 16 (next tap along N) and
 // LBO = 160 (next image row = next 8 pixels along K) one MMA covers the three taps of a kernel row (N = 32, the
-// fourth block is ignored), so a patch is visited once (not once per kernel column) and dZ is read once.
+// fourth block is ignored), so a patch is visited once (not once per kernel column) and dZ is read once.  And since a halo
+// row is 10 such blocks long, block 10 r + s is tap (r, s): ONE N = 184 MMA per 16 pixels covers all nine taps (`c8_rows3`,
+// 92 cycles instead of 3 x 40; the blocks in between multiply pixels further right and are never stored).
 //
 // Row stack (`stack`, N tile of 64 channels with X on N: conv2_1): the three vertical taps of the X halo box are three
 // 64-column blocks of ONE N = 192 MMA -- an MN-major operand's 64-element blocks may sit anywhere LBO bytes apart, and
-// LBO = one image row of the patch makes block r the box seen through kernel row r.  A narrow MMA costs ~47 + N/4 cycles
-// whatever it computes (tools/exp/mma_major.cu: 71 / 79 / 128 cycles for N = 64 / 128 / 256), so one N = 192 MMA
-// (~96 cycles) replaces three N = 64 ones (213).
+// LBO = one image row of the patch makes block r the box seen through kernel row r.  An M = 128 MMA costs
+// max(N / 2, 32 + N / 4) cycles whatever its operands' major-ness (tools/exp/mma_side.cu, mma_major.cu: 48 / 64 / 96 / 128
+// cycles for N = 64 / 128 / 192 / 256), so one N = 192 MMA (96 cycles, tensor-bound) replaces three N = 64 ones (144).
 //
 // X on M with a narrow dZ (`zstack`: side_prep, Cout = 16): the same stack with the vertical shift moved to dZ (below); its
 // 16 channels sit in 64-column blocks (TMA zero-fills the rest), so a kernel column is one N = 192 MMA instead of three
-// N = 16 ones (~51 cycles each: a narrow MMA is bound by reading its 128-row A tile).
+// N = 16 ones (39 cycles each: a narrow MMA is bound by reading its 128-row A tile).
 //
 // Cout <= 64 with X on M (`one_pass`: conv1_2, and side_prep by default): the stack with the vertical shift moved to dZ -- sum_p dZ[p] X[p + (dy, dx)]
 // = sum_q dZ[q - (dy, 0)] X[q + (0, dx)] -- so B = dZ halo box (three row shifts, N = 192) and A = X under two horizontal
